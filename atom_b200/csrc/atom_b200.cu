@@ -1,0 +1,312 @@
+// atom_b200.cu -- C ABI (include/atom_b200.h) and host-side launch logic of libatom_b200.so.
+//
+// No torch types, no allocation, no synchronisation: every entry point validates its arguments, builds the TMA
+// descriptors it needs on the host (cached by (pointer, shape)) and enqueues kernels on the caller's stream.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/atom_b200.h"
+#include "gemm_i4_sm100.cuh"
+#include "kv_kernels.cuh"
+#include "quant_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define ATOM_REQUIRE(cond, ...) \
+  do { if (!(cond)) return fail(ATOM_E_INVALID, __VA_ARGS__); } while (0)
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ATOM_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return ATOM_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; uint64_t inner, rows, pitch; uint32_t box_inner, box_rows, swizzle;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && rows == o.rows && pitch == o.pitch && box_inner == o.box_inner &&
+           box_rows == o.box_rows && swizzle == o.swizzle;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.rows); mix(k.pitch); mix(k.box_inner); mix(k.box_rows); mix(k.swizzle);
+    return h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D byte tensor [rows][inner] with row pitch `pitch`; box = box_rows x box_inner bytes; OOB rows read as zero.
+int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch, uint32_t box_inner,
+             uint32_t box_rows, bool swizzle128) {
+  MapKey key{ptr, inner, rows, pitch, box_inner, box_rows, swizzle128 ? 1u : 0u};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return ATOM_OK; }
+  }
+  EncodeFn fn = encode_fn();
+  if (!fn) return fail(ATOM_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {pitch};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ATOM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, *out);
+  return ATOM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+struct GemmOperands {
+  const void *a, *b, *ak, *bk;
+  int64_t M, N, K;
+};
+
+template <bool kSwap, int BN, int kPack, int kExp, int kSplit, bool kO4>
+int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
+  using C = atom::GemmCfg<kSwap, BN, kPack, kExp, kSplit, kO4>;
+  auto kern = atom::gemm_i4_kernel<kSwap, BN, kPack, kExp, kSplit, kO4>;
+  static bool attr_set = false;   // per instantiation; benign race (idempotent)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(ATOM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const uint64_t kp = (uint64_t)(op.K - 128) / 2;
+  // MMA-M operand = kSwap ? weights : tokens
+  const void* p4 = kSwap ? op.b : op.a;  const void* q4 = kSwap ? op.a : op.b;
+  const void* p8 = kSwap ? op.bk : op.ak; const void* q8 = kSwap ? op.ak : op.bk;
+  const uint64_t prow = kSwap ? op.N : op.M, qrow = kSwap ? op.M : op.N;
+  CUtensorMap tp4, tq4, tp8, tq8;
+  int rc;
+  if ((rc = make_map(&tp4, p4, kp, prow, kp, 64, C::BM, false))) return rc;
+  if ((rc = make_map(&tq4, q4, kp, qrow, kp, 64, BN, false))) return rc;
+  if ((rc = make_map(&tp8, p8, 128, prow, 128, 128, C::BM, true))) return rc;
+  if ((rc = make_map(&tq8, q8, 128, qrow, 128, 128, BN, true))) return rc;
+
+  const int ch_tile = kSwap ? C::BM : BN, tok_tile = kSwap ? BN : C::BM;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((op.N + ch_tile - 1) / ch_tile), (unsigned)((op.M + tok_tile - 1) / tok_tile), kSplit);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = kSplit;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tp4, tq4, tp8, tq8, args);
+  if (e != cudaSuccess) return fail(ATOM_E_CUDA, "gemm_i4 launch: %s", cudaGetErrorString(e));
+  return ATOM_OK;
+}
+
+template <bool kO4>
+int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
+  const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
+  if (!skinny) return launch_gemm<false, 128, 4, 3, 1, kO4>(op, args, stream);
+  // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not
+  // cover the machine (the kernel is HBM-bound on the weights: more CTAs = more bytes in flight)
+  const int64_t ch_tiles = (op.N + 127) / 128;
+  const int groups = args.G + 1;
+  const bool split = !(flags & ATOM_GEMM_NO_SPLITK) && groups >= 8 && ch_tiles * ((op.M + 63) / 64) < 120;
+  if (op.M <= 16) return split ? launch_gemm<true, 16, 8, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 16, 8, 3, 1, kO4>(op, args, stream);
+  if (op.M <= 32) return split ? launch_gemm<true, 32, 8, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 32, 8, 3, 1, kO4>(op, args, stream);
+  return split ? launch_gemm<true, 64, 6, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 64, 6, 3, 1, kO4>(op, args, stream);
+}
+
+int gemm_common(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
+                const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d, void* d_scale,
+                int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream, bool o4) {
+  ATOM_REQUIRE(a && b && a_scale && b_scale && a_keeper && b_keeper && a_keeper_scale && b_keeper_scale && d,
+               "gemm_i4: null pointer argument");
+  ATOM_REQUIRE(M > 0 && N > 0, "gemm_i4: M=%lld N=%lld must be positive", (long long)M, (long long)N);
+  ATOM_REQUIRE(K >= 256 && K % 128 == 0, "gemm_i4: K=%lld must be a multiple of 128 and >= 256 (INT4 groups + 128 keeper)", (long long)K);
+  ATOM_REQUIRE(N % 8 == 0, "gemm_i4: N=%lld must be a multiple of 8", (long long)N);
+  ATOM_REQUIRE(!o4 || (N % 128 == 0 && d_scale), "gemm_i4_o4: N=%lld must be a multiple of 128 (one head per scale)", (long long)N);
+  ATOM_REQUIRE(aligned16(a) && aligned16(b) && aligned16(a_keeper) && aligned16(b_keeper) && aligned16(d),
+               "gemm_i4: operand pointers must be 16-byte aligned");
+  ATOM_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 24), "gemm_i4: dimension too large");
+  GemmOperands op{a, b, a_keeper, b_keeper, M, N, K};
+  atom::GemmArgs args{};
+  args.a_scale = (const __half*)a_scale; args.b_scale = (const __half*)b_scale;
+  args.a_keeper_scale = (const __half*)a_keeper_scale; args.b_keeper_scale = (const __half*)b_keeper_scale;
+  args.d = o4 ? nullptr : (__half*)d; args.d4 = o4 ? (uint8_t*)d : nullptr; args.d_scale = (__half2*)d_scale;
+  args.M = (int)M; args.N = (int)N; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M);
+  return o4 ? gemm_dispatch<true>(op, args, flags, (cudaStream_t)stream) : gemm_dispatch<false>(op, args, flags, (cudaStream_t)stream);
+}
+
+int quant_check(const char* what, int seq_len, int hidden, const void* o8, const void* o4, const void* s8, const void* s4) {
+  ATOM_REQUIRE(seq_len > 0, "%s: seq_len=%d must be positive", what, seq_len);
+  ATOM_REQUIRE(hidden >= 256 && hidden % 128 == 0 && hidden <= 65536, "%s: hidden_dim=%d must be a multiple of 128 in [256, 65536]", what, hidden);
+  ATOM_REQUIRE(o8 && o4 && s8 && s4, "%s: null output pointer", what);
+  return ATOM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int atom_version(void) { return 100; }
+const char* atom_last_error(void) { return g_err.c_str(); }
+int atom_scale_index(int row) { return atom::scale_index(row); }
+int atom_scale_size(int rows) { return atom::scale_size(rows); }
+
+int atom_reorder_fp16_i4(const void* hidden, const void* reorder_index, int seq_len, int hidden_dim, void* o_outliers,
+                         void* o_norms, void* outlier_scales, void* norm_scales, void* stream) {
+  int rc = quant_check("reorder_fp16_i4", seq_len, hidden_dim, o_outliers, o_norms, outlier_scales, norm_scales);
+  if (rc) return rc;
+  ATOM_REQUIRE(hidden && reorder_index && aligned16(hidden), "reorder_fp16_i4: null or misaligned input");
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(atom::reorder_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072); attr_set = true; }
+  atom::reorder_quant_kernel<<<seq_len, 256, (size_t)hidden_dim * 2, (cudaStream_t)stream>>>(
+      (const __half*)hidden, (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms,
+      (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
+  return check_launch("reorder_fp16_i4");
+}
+
+int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, const void* reorder_index, int seq_len,
+                         int hidden_dim, void* o_outliers, void* o_norms, void* outlier_scales, void* norm_scales,
+                         void* stream) {
+  int rc = quant_check("rmsnorm_fp16_i4", seq_len, hidden_dim, o_outliers, o_norms, outlier_scales, norm_scales);
+  if (rc) return rc;
+  ATOM_REQUIRE(hidden && weight && reorder_index && aligned16(hidden), "rmsnorm_fp16_i4: null or misaligned input");
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(atom::rmsnorm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 512); attr_set = true; }
+  atom::rmsnorm_quant_kernel<<<seq_len, 128, (size_t)hidden_dim * 2 + 512, (cudaStream_t)stream>>>(
+      (const __half*)hidden, (const __half*)weight, eps, (const int16_t*)reorder_index, seq_len, hidden_dim,
+      (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
+  return check_launch("rmsnorm_fp16_i4");
+}
+
+int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, int hidden_dim, void* o_outliers, void* o_norms,
+                          void* outlier_scales, void* norm_scales, void* stream) {
+  int rc = quant_check("activate_fp16_i4", seq_len, hidden_dim, o_outliers, o_norms, outlier_scales, norm_scales);
+  if (rc) return rc;
+  ATOM_REQUIRE(a && b && aligned16(a) && aligned16(b), "activate_fp16_i4: null or misaligned input");
+  const long long units = (long long)seq_len * (hidden_dim / 128);
+  atom::activate_quant_kernel<<<(unsigned)((units + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)a, (const __half*)b, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms,
+      (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
+  return check_launch("activate_fp16_i4");
+}
+
+int atom_gemm_i4_o16(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
+                     const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d, int64_t M,
+                     int64_t N, int64_t K, uint32_t flags, void* stream) {
+  return gemm_common(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, d, nullptr, M, N, K,
+                     flags, stream, false);
+}
+
+int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
+                    const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d,
+                    void* d_scale, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream) {
+  return gemm_common(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, d, d_scale, M, N, K,
+                     flags, stream, true);
+}
+
+static int kv_check(const char* what, const void* data, const void* param, const void* indptr, const void* indices,
+                    const void* last, int L, int layer, int H, int P, int B) {
+  ATOM_REQUIRE(data && param && indptr && indices && last, "%s: null pointer argument", what);
+  ATOM_REQUIRE(L > 0 && layer >= 0 && layer < L, "%s: layer_idx=%d out of range [0,%d)", what, layer, L);
+  ATOM_REQUIRE(H > 0 && P > 0 && B > 0, "%s: num_heads=%d page_size=%d batch_size=%d must be positive", what, H, P, B);
+  return ATOM_OK;
+}
+
+int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, const void* kv_param, const void* kv_indptr,
+                         const void* kv_indices, const void* last_page_offset, int num_layers, int layer_idx,
+                         int num_heads, int page_size, int batch_size, void* stream) {
+  int rc = kv_check("batch_decode_i4", kv_data, kv_param, kv_indptr, kv_indices, last_page_offset, num_layers, layer_idx,
+                    num_heads, page_size, batch_size);
+  if (rc) return rc;
+  ATOM_REQUIRE(o && q, "batch_decode_i4: null q/o");
+  ATOM_REQUIRE(page_size <= 128, "batch_decode_i4: page_size=%d > 128 unsupported", page_size);
+  atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
+                  (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
+  const size_t smem = (size_t)page_size * 64 * 8 + 64 * 8 + 4 * 4 * 34 * 4;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(atom::batch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 64 * 8 + 4096); attr_set = true; }
+  atom::batch_decode_kernel<<<dim3(batch_size, num_heads), atom::DEC_THREADS, smem, (cudaStream_t)stream>>>(
+      (__half*)o, (const __half*)q, kv);
+  return check_launch("batch_decode_i4");
+}
+
+int atom_append_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,
+                      const void* last_page_offset, const void* k, const void* v, const void* k_param,
+                      const void* v_param, int num_layers, int layer_idx, int num_heads, int page_size, int batch_size,
+                      void* stream) {
+  int rc = kv_check("append_kv_i4", kv_data, kv_param, kv_indptr, kv_indices, last_page_offset, num_layers, layer_idx,
+                    num_heads, page_size, batch_size);
+  if (rc) return rc;
+  ATOM_REQUIRE(k && v && k_param && v_param, "append_kv_i4: null k/v");
+  atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
+                  (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
+  const long long threads = (long long)batch_size * num_heads * 16;
+  atom::append_kv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      kv, (const uint8_t*)k, (const uint8_t*)v, (const __half2*)k_param, (const __half2*)v_param, nullptr, batch_size);
+  return check_launch("append_kv_i4");
+}
+
+int atom_init_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,
+                    const void* last_page_offset, const void* k, const void* v, const void* k_param,
+                    const void* v_param, const void* seqlen_indptr, int total_tokens, int num_layers, int layer_idx,
+                    int num_heads, int page_size, int batch_size, void* stream) {
+  int rc = kv_check("init_kv_i4", kv_data, kv_param, kv_indptr, kv_indices, last_page_offset, num_layers, layer_idx,
+                    num_heads, page_size, batch_size);
+  if (rc) return rc;
+  ATOM_REQUIRE(k && v && k_param && v_param && seqlen_indptr, "init_kv_i4: null k/v/seqlen_indptr");
+  if (total_tokens <= 0) return ATOM_OK;
+  atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
+                  (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
+  const long long threads = (long long)total_tokens * num_heads * 16;
+  atom::append_kv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      kv, (const uint8_t*)k, (const uint8_t*)v, (const __half2*)k_param, (const __half2*)v_param,
+      (const int32_t*)seqlen_indptr, total_tokens);
+  return check_launch("init_kv_i4");
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""Operator API -- mirrors /root/reference/e2e/punica-atom/punica/ops/__init__.py (names, argument order,
+output allocation and return tuples) on top of the sm_100a kernels in libatom_b200.so.
+
+Differences from the reference (all widening, none changes a result):
+  * kernels run on torch's current CUDA stream (the reference uses the legacy default stream);
+  * hidden_dim is any multiple of 128 (reference: 4096 for reorder/rmsnorm, 11008 for activate);
+  * errors raise RuntimeError with the library's message instead of being silently ignored.
+"""
+import torch
+
+from . import _lib
+
+__all__ = [
+    "batch_decode_i4", "append_kv_i4", "init_kv_i4", "activate_fp16_i4", "dense_layer_gemm_i4_fp16",
+    "dense_layer_gemm_i4_o4", "rmsnorm_fp16_i4", "reorder_fp16_i4", "scale_size",
+]
+
+GEMM_AUTO, GEMM_NO_SPLITK, GEMM_FORCE_TALL, GEMM_FORCE_SKINNY = 0, 1, 2, 4
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda):
+            raise RuntimeError("atom_b200.ops: all tensors must live on a CUDA device (there is no CPU path)")
+        if not t.is_contiguous():
+            raise RuntimeError("atom_b200.ops: tensors must be contiguous")
+
+
+def scale_size(x):
+    """ops/__init__.py:137-138"""
+    return ((x) // 16 * 64 + 64 - (1 - (x % 16) // 8) * (8 - (x % 8)) * 8)
+
+
+def _quant_outputs(bs, hidden_dim, device):
+    group_size = 128
+    o_outlier = torch.empty((bs, group_size), dtype=torch.int8, device=device)
+    o_norms = torch.empty((bs, (hidden_dim - group_size) // 2), dtype=torch.int8, device=device)
+    outlier_scales = torch.empty((scale_size(bs),), dtype=torch.float16, device=device)
+    norm_scales = torch.empty((hidden_dim // group_size - 1, scale_size(bs)), dtype=torch.float16, device=device)
+    return o_outlier, o_norms, outlier_scales, norm_scales
+
+
+def reorder_fp16_i4(hidden_states, reorder_index):
+    """ops/__init__.py:200-219"""
+    _req_cuda(hidden_states, reorder_index)
+    bs, hidden_dim = hidden_states.shape
+    out = _quant_outputs(bs, hidden_dim, hidden_states.device)
+    with torch.cuda.device(hidden_states.device):
+        _lib.check(_lib.lib().atom_reorder_fp16_i4(hidden_states.data_ptr(), reorder_index.data_ptr(), bs, hidden_dim,
+                                                   out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                                   out[3].data_ptr(), _stream(hidden_states)), "reorder_fp16_i4")
+    return out
+
+
+def rmsnorm_fp16_i4(hidden_states, weight, reorder_index, eps):
+    """ops/__init__.py:179-198.  `weight` may be fp32 (LlamaRMSNormInt4 keeps torch.ones fp32, llama.py:237); the
+    reference reinterprets its storage as half -- here it is converted, which is what was meant."""
+    _req_cuda(hidden_states, weight, reorder_index)
+    if weight.dtype != torch.float16:
+        weight = weight.to(torch.float16)
+    bs, hidden_dim = hidden_states.shape
+    out = _quant_outputs(bs, hidden_dim, hidden_states.device)
+    with torch.cuda.device(hidden_states.device):
+        _lib.check(_lib.lib().atom_rmsnorm_fp16_i4(hidden_states.data_ptr(), weight.data_ptr(), float(eps),
+                                                   reorder_index.data_ptr(), bs, hidden_dim, out[0].data_ptr(),
+                                                   out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                                   _stream(hidden_states)), "rmsnorm_fp16_i4")
+    return out
+
+
+def activate_fp16_i4(a, b):
+    """ops/__init__.py:141-157"""
+    _req_cuda(a, b)
+    bs, hidden_dim = a.shape
+    out = _quant_outputs(bs, hidden_dim, a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().atom_activate_fp16_i4(a.data_ptr(), b.data_ptr(), bs, hidden_dim, out[0].data_ptr(),
+                                                    out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                                    _stream(a)), "activate_fp16_i4")
+    return out
+
+
+def dense_layer_gemm_i4_fp16(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, flags=GEMM_AUTO):
+    """ops/__init__.py:160-168; dims as punica_ops.cc:236-237 (K = a.size(1)*2 + a_keeper.size(1))."""
+    _req_cuda(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale)
+    m, n = a.size(0), b.size(0)
+    k = a.size(1) * 2 + a_keeper.size(1)
+    d = torch.empty((m, n), dtype=torch.float16, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().atom_gemm_i4_o16(a.data_ptr(), b.data_ptr(), a_scale.data_ptr(), b_scale.data_ptr(),
+                                               a_keeper.data_ptr(), b_keeper.data_ptr(), a_keeper_scale.data_ptr(),
+                                               b_keeper_scale.data_ptr(), d.data_ptr(), m, n, k, flags, _stream(a)),
+                   "dense_layer_gemm_i4_fp16")
+    return d
+
+
+def dense_layer_gemm_i4_o4(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, flags=GEMM_AUTO):
+    """ops/__init__.py:171-176"""
+    _req_cuda(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale)
+    m, n = a.size(0), b.size(0)
+    k = a.size(1) * 2 + a_keeper.size(1)
+    d = torch.empty((m, n // 2), dtype=torch.uint8, device=a.device)
+    assert n % 128 == 0
+    d_scale = torch.empty((m, n // 128 * 2), dtype=torch.float16, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().atom_gemm_i4_o4(a.data_ptr(), b.data_ptr(), a_scale.data_ptr(), b_scale.data_ptr(),
+                                              a_keeper.data_ptr(), b_keeper.data_ptr(), a_keeper_scale.data_ptr(),
+                                              b_keeper_scale.data_ptr(), d.data_ptr(), d_scale.data_ptr(), m, n, k,
+                                              flags, _stream(a)), "dense_layer_gemm_i4_o4")
+    return d, d_scale
+
+
+def _kv_dims(kv):
+    # CHECK_DIM(6, kv_data) etc., punica_ops.cc:93-112
+    if kv.data.dim() != 6 or kv.param.dim() != 6:
+        raise RuntimeError("kv_data / kv_param must be 6-D [pages, L, 2, H, P, D]")
+    if kv.data.dtype != torch.uint8 or kv.param.dtype != torch.float16:
+        raise RuntimeError("kv_data must be uint8 and kv_param float16")
+    if kv.data.size(5) * 2 != 128:
+        raise RuntimeError("head_dim must be 128")
+    return kv.data.size(1), kv.data.size(3), kv.data.size(4)
+
+
+def batch_decode_i4(q, kv, layer_idx):
+    """ops/__init__.py:21-32"""
+    _req_cuda(q, kv.data, kv.param, kv.indptr, kv.indicies, kv.last_page_offset)
+    L, H, P = _kv_dims(kv)
+    if q.dim() != 3 or q.size(1) != H or q.size(2) != 128 or kv.indptr.size(0) != q.size(0) + 1 or \
+            kv.last_page_offset.size(0) != q.size(0):
+        raise RuntimeError("batch_decode_i4: shape mismatch")
+    o = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.lib().atom_batch_decode_i4(o.data_ptr(), q.data_ptr(), kv.data.data_ptr(), kv.param.data_ptr(),
+                                                   kv.indptr.data_ptr(), kv.indicies.data_ptr(),
+                                                   kv.last_page_offset.data_ptr(), L, layer_idx, H, P, q.size(0),
+                                                   _stream(q)), "batch_decode_i4")
+    return o
+
+
+def init_kv_i4(kv, k, v, k_param, v_param, seqlen_indptr, layer_idx):
+    """ops/__init__.py:35-46"""
+    _req_cuda(kv.data, kv.param, kv.indptr, kv.indicies, kv.last_page_offset, k, v, k_param, v_param, seqlen_indptr)
+    L, H, P = _kv_dims(kv)
+    B = kv.last_page_offset.size(0)
+    if kv.indptr.size(0) != B + 1 or seqlen_indptr.size(0) != B + 1:
+        raise RuntimeError("init_kv_i4: indptr sizes do not match the batch")
+    with torch.cuda.device(k.device):
+        _lib.check(_lib.lib().atom_init_kv_i4(kv.data.data_ptr(), kv.param.data_ptr(), kv.indptr.data_ptr(),
+                                              kv.indicies.data_ptr(), kv.last_page_offset.data_ptr(), k.data_ptr(),
+                                              v.data_ptr(), k_param.data_ptr(), v_param.data_ptr(),
+                                              seqlen_indptr.data_ptr(), k.size(0), L, layer_idx, H, P, B, _stream(k)),
+                   "init_kv_i4")
+
+
+def append_kv_i4(kv, k, v, k_param, v_param, layer_idx):
+    """ops/__init__.py:49-59"""
+    _req_cuda(kv.data, kv.param, kv.indptr, kv.indicies, kv.last_page_offset, k, v, k_param, v_param)
+    L, H, P = _kv_dims(kv)
+    B = k.size(0)
+    if kv.indptr.size(0) != B + 1 or kv.last_page_offset.size(0) != B or k.shape != v.shape:
+        raise RuntimeError("append_kv_i4: shape mismatch")
+    with torch.cuda.device(k.device):
+        _lib.check(_lib.lib().atom_append_kv_i4(kv.data.data_ptr(), kv.param.data_ptr(), kv.indptr.data_ptr(),
+                                                kv.indicies.data_ptr(), kv.last_page_offset.data_ptr(), k.data_ptr(),
+                                                v.data_ptr(), k_param.data_ptr(), v_param.data_ptr(), L, layer_idx, H,
+                                                P, B, _stream(k)), "append_kv_i4")

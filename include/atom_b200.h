@@ -1,0 +1,106 @@
+/*
+ * atom_b200.h -- C ABI of libatom_b200.so: the B200 (sm_100a) implementation of the efeslab/Atom W4A4 hot path.
+ *
+ * One entry point per function that the reference binds into Python through
+ * pybind11 (/root/reference/e2e/punica-atom/punica/ops/csrc/punica_ops.cc:270-279).  Plain pointers and sizes only;
+ * every pointer is a DEVICE pointer owned by the caller, outputs are pre-allocated by the caller (exactly as
+ * punica/ops/__init__.py:21-219 does with torch.empty) and the library keeps no reference to them.
+ *
+ * Conventions
+ *   - return value: 0 on success, negative ATOM_E_* otherwise; atom_last_error() returns a thread-local message.
+ *     (The reference returns void and never checks cudaGetLastError; its KV ops raise via TORCH_CHECK.)
+ *   - `stream` is a cudaStream_t passed as void*.  The reference launches on the legacy default stream; pass the
+ *     caller's current stream (NULL = legacy default).  All entry points are asynchronous and graph-capturable
+ *     (no allocation, no synchronisation; TMA descriptors are built on the host per call).
+ *   - layouts are the reference's, unchanged.
+ */
+#ifndef ATOM_B200_H_
+#define ATOM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ATOM_API __attribute__((visibility("default")))
+#else
+#define ATOM_API
+#endif
+
+#define ATOM_OK 0
+#define ATOM_E_INVALID (-1) /* bad shape / alignment / null pointer */
+#define ATOM_E_CUDA (-2)    /* a CUDA runtime or driver call failed  */
+#define ATOM_E_UNSUPPORTED (-3)
+
+/* gemm flags */
+#define ATOM_GEMM_AUTO 0u
+#define ATOM_GEMM_NO_SPLITK 1u   /* bit-exact accumulation order (groups 0..G-1 then keeper) even for small M */
+#define ATOM_GEMM_FORCE_TALL 2u  /* tokens on the MMA-M axis regardless of M */
+#define ATOM_GEMM_FORCE_SKINNY 4u /* channels on the MMA-M axis (requires M <= 128 per tile; any M works) */
+
+ATOM_API int atom_version(void);
+ATOM_API const char* atom_last_error(void);
+
+/* Reorder.cuh:39-50 / punica/ops/__init__.py:137 -- the scale layout contract shared by quantise kernels and GEMM */
+ATOM_API int atom_scale_index(int row);
+ATOM_API int atom_scale_size(int rows);
+
+/* replaces reorder_fp16_i4 (punica_ops.cc:251-260 -> run_reorder_fp16_i4<128,4096>, Reorder.cuh:205-228)
+ *   hidden        f16 [seq_len, hidden_dim]      reorder_index i16 [hidden_dim]
+ *   o_outliers    i8  [seq_len, 128]             o_norms       u8  [seq_len, (hidden_dim-128)/2]
+ *   outlier_scales f16 [scale_size(seq_len)]     norm_scales   f16 [hidden_dim/128-1, scale_size(seq_len)]
+ * hidden_dim: any multiple of 128 (the reference is compiled for 4096 only). */
+ATOM_API int atom_reorder_fp16_i4(const void* hidden, const void* reorder_index, int seq_len, int hidden_dim, void* o_outliers,
+                         void* o_norms, void* outlier_scales, void* norm_scales, void* stream);
+
+/* replaces rmsnorm_fp16_i4 (punica_ops.cc:239-249 -> run_rmsnorm_fp16_i4<128,4096>, RMSNorm.cuh:255-285) */
+ATOM_API int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, const void* reorder_index, int seq_len,
+                         int hidden_dim, void* o_outliers, void* o_norms, void* outlier_scales, void* norm_scales,
+                         void* stream);
+
+/* replaces activate_fp16_i4 (punica_ops.cc:73-80 -> run_activate_fp16_i4<128,11008>, Activate.cuh:194-218) */
+ATOM_API int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, int hidden_dim, void* o_outliers, void* o_norms,
+                          void* outlier_scales, void* norm_scales, void* stream);
+
+/* replaces dense_layer_gemm_i4_fp16 (punica_ops.cc:226-237 -> DenseLayerGEMM_i4<nv_half>, DenseLayerGEMM_i4.cu:723-793)
+ *   a u8 [M,(K-128)/2]  b u8 [N,(K-128)/2]  a_scale f16 [K/128-1, scale_size(M)]  b_scale f16 [K/128-1, N]
+ *   a_keeper i8 [M,128] b_keeper i8 [N,128] a_keeper_scale f16 [scale_size(M)]    b_keeper_scale f16 [N]
+ *   d f16 [M,N].   K includes the 128 keeper channels (as in the e2e launcher).  N % 8 == 0, K % 128 == 0, K >= 256. */
+ATOM_API int atom_gemm_i4_o16(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
+                     const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d, int64_t M,
+                     int64_t N, int64_t K, uint32_t flags, void* stream);
+
+/* replaces dense_layer_gemm_i4_o4 (punica_ops.cc:211-224 -> DenseLayerGEMM_i4_o4, DenseLayerGEMM_i4_o4.cu:808-856)
+ *   d u8 [M, N/2] (asymmetric INT4 per 128-column head), d_scale f16 [M, N/128, 2] = (scale, zero).  N % 128 == 0. */
+ATOM_API int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
+                    const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d,
+                    void* d_scale, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream);
+
+/* replaces batch_decode_i4 (punica_ops.cc:82-120 -> FlashInferBatchDecodeKernel_i4<128>, flashinfer_impl.cuh:9-46)
+ *   o,q f16 [B,H,128]  kv_data u8 [pages,L,2,H,P,64]  kv_param f16 [pages,L,2,H,P,2]
+ *   kv_indptr i32 [B+1]  kv_indices i32 [nnz]  last_page_offset i32 [B] */
+ATOM_API int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, const void* kv_param, const void* kv_indptr,
+                         const void* kv_indices, const void* last_page_offset, int num_layers, int layer_idx,
+                         int num_heads, int page_size, int batch_size, void* stream);
+
+/* replaces append_kv_i4 (punica_ops.cc:166-209 -> FlashInferAppendKvKernel_i4<128>, flashinfer_impl.cuh:73-96)
+ *   k,v u8 [B,H,64]  k_param,v_param f16 [B,H,2] */
+ATOM_API int atom_append_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,
+                      const void* last_page_offset, const void* k, const void* v, const void* k_param,
+                      const void* v_param, int num_layers, int layer_idx, int num_heads, int page_size, int batch_size,
+                      void* stream);
+
+/* replaces init_kv_i4 (punica_ops.cc:122-164 -> FlashInferInitKvKernel_i4<128>, flashinfer_impl.cuh:48-71)
+ *   k,v u8 [sum(len),H,64]  params f16 [sum(len),H,2]  seqlen_indptr i32 [B+1]; total_tokens = seqlen_indptr[B] */
+ATOM_API int atom_init_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,
+                    const void* last_page_offset, const void* k, const void* v, const void* k_param,
+                    const void* v_param, const void* seqlen_indptr, int total_tokens, int num_layers, int layer_idx,
+                    int num_heads, int page_size, int batch_size, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATOM_B200_H_ */

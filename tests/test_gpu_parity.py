@@ -1,0 +1,195 @@
+"""GPU parity suite (-m gpu): every kernel, called through the C ABI (atom_b200.ops -> libatom_b200.so), against
+the CPU oracle on the same seeded inputs.  Integer / packing / index paths are bit-exact; FP paths carry the
+tolerance written next to each assert.  The companion suite test_gpu_vs_reference.py compares with the
+reference's own CUDA kernels (oracle/_ref) on the same GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def nib_diff(p, q):
+    return np.abs(O.unpack_int4(p).astype(np.int32) - O.unpack_int4(q).astype(np.int32))
+
+
+def _quant_inputs(rng, m, h):
+    x = (rng.standard_normal((m, h)) * np.where(rng.random((1, h)) > 0.97, 12.0, 1.0)).astype(np.float16)
+    idx = rng.permutation(h).astype(np.int16)
+    return x, idx
+
+
+def _cmp_quant(out, ref, exact):
+    o8, o4, s8, s4 = [t.cpu().numpy() for t in out]
+    r8, r4, rs8, rs4 = ref
+    m = r8.shape[0]
+    if exact:
+        assert np.array_equal(o8, r8)
+        assert np.array_equal(o4.view(np.uint8), r4)
+        assert np.array_equal(O.a_scale_from_layout(s8, m).view(np.uint16), O.a_scale_from_layout(rs8, m).view(np.uint16))
+        assert np.array_equal(O.a_scale_from_layout(s4, m).view(np.uint16), O.a_scale_from_layout(rs4, m).view(np.uint16))
+    else:  # approximate rsqrtf / expf on the GPU: +-1 LSB, the reference's own tolerance (test_Reorder.cu:269-318)
+        assert np.abs(o8.astype(np.int32) - r8.astype(np.int32)).max() <= 1
+        assert nib_diff(o4.view(np.uint8), r4).max() <= 1
+        assert (nib_diff(o4.view(np.uint8), r4) != 0).mean() < 5e-3
+        assert np.allclose(O.a_scale_from_layout(s4, m).astype(np.float32), O.a_scale_from_layout(rs4, m).astype(np.float32), rtol=2e-3)
+        assert np.allclose(O.a_scale_from_layout(s8, m).astype(np.float32), O.a_scale_from_layout(rs8, m).astype(np.float32), rtol=2e-3)
+    # replicas of the scale layout: all four copies written
+    idx = np.array([O.scale_index(r) for r in range(m)])
+    for j in range(1, 4):
+        assert np.array_equal(s8[idx + 2 * j].view(np.uint16), s8[idx].view(np.uint16))
+        assert np.array_equal(s4[:, idx + 2 * j].view(np.uint16), s4[:, idx].view(np.uint16))
+
+
+@pytest.mark.parametrize("m,h", [(1, 4096), (7, 4096), (16, 4096), (21, 4096), (129, 4096), (33, 5120), (5, 8192), (3, 256)])
+def test_reorder_bit_exact(m, h):
+    from atom_b200 import ops
+    rng = np.random.default_rng(m * 131 + h)
+    x, idx = _quant_inputs(rng, m, h)
+    _cmp_quant(ops.reorder_fp16_i4(T(x), T(idx)), O.reorder_fp16_i4(x, idx), exact=True)
+
+
+@pytest.mark.parametrize("m,h", [(1, 4096), (7, 4096), (16, 4096), (40, 4096), (9, 5120), (4, 8192)])
+def test_rmsnorm_quant(m, h):
+    from atom_b200 import ops
+    rng = np.random.default_rng(m * 17 + h)
+    x, idx = _quant_inputs(rng, m, h)
+    w = (1 + 0.2 * rng.standard_normal(h)).astype(np.float16)
+    _cmp_quant(ops.rmsnorm_fp16_i4(T(x), T(w), T(idx), 1e-5), O.rmsnorm_fp16_i4(x, w, idx, 1e-5), exact=False)
+
+
+@pytest.mark.parametrize("m,h", [(1, 11008), (7, 11008), (16, 11008), (5, 13824), (3, 22016), (33, 4096), (2, 2816)])
+def test_activate_quant(m, h):
+    from atom_b200 import ops
+    rng = np.random.default_rng(m * 29 + h)
+    a = (rng.standard_normal((m, h)) * 2).astype(np.float16)
+    b = (rng.standard_normal((m, h)) * 2).astype(np.float16)
+    _cmp_quant(ops.activate_fp16_i4(T(a), T(b)), O.activate_fp16_i4(a, b), exact=False)
+
+
+def _ulp_diff(a, b):
+    """distance in fp16 ulps between two float16 arrays (monotone integer mapping)"""
+    def key(x):
+        u = x.view(np.uint16).astype(np.int32)
+        return np.where(u & 0x8000, 0x8000 - u, u)
+    return np.abs(key(a) - key(b))
+
+
+GEMM_CASES = [
+    # (M, N, K, flags, exact)   flags: 0 auto, 1 no split-K, 2 force tall, 4 force skinny
+    (16, 256, 512, 2, True), (128, 128, 256, 2, True), (7, 128, 384, 2, True), (129, 384, 1024, 2, True),
+    (300, 256, 4096, 2, True),
+    (16, 256, 512, 5, True), (7, 128, 384, 5, True), (1, 128, 256, 5, True), (33, 256, 1024, 5, True),
+    (64, 384, 4096, 5, True), (16, 4096, 4096, 1, True),
+    (16, 4096, 4096, 0, False), (32, 1024, 4096, 0, False), (48, 512, 11008, 0, False), (5, 128, 2048, 0, False),
+    (130, 2752, 1024, 0, True),
+]
+
+
+@pytest.mark.parametrize("m,n,k,flags,exact", GEMM_CASES)
+def test_gemm_o16(m, n, k, flags, exact):
+    from atom_b200 import ops
+    t = O.make_gemm_inputs(m, n, k, seed=m * 7919 + n * 31 + k, pair_shared=(m % 2 == 0))
+    d = ops.dense_layer_gemm_i4_fp16(*[T(x) for x in t], flags=flags).cpu().numpy()
+    rows = None if m * n * k <= (1 << 28) else sorted(set(np.random.default_rng(1).integers(0, m, 24).tolist() + [0, m - 1]))
+    ref = O.gemm_i4_o16(*t, rows=rows)
+    got = d if rows is None else d[rows]
+    if exact:   # same association as the reference: groups in order, keeper last -> bit exact
+        assert np.array_equal(got.view(np.uint16), ref.view(np.uint16)), f"max ulp {_ulp_diff(got, ref).max()}"
+    else:       # split-K: FP32 partial sums are added in a different order -> at most 1 fp16 ulp, rarely
+        ud = _ulp_diff(got, ref)
+        assert ud.max() <= 1 and (ud != 0).mean() < 0.02
+        assert np.allclose(got.astype(np.float32), ref.astype(np.float32), rtol=1e-3, atol=1e-3 * np.abs(ref.astype(np.float32)).mean())
+
+
+@pytest.mark.parametrize("m,n,k,flags", [(16, 256, 512, 2), (130, 384, 1024, 2), (16, 256, 512, 5), (7, 128, 1024, 5),
+                                         (48, 4096, 4096, 1), (16, 4096, 4096, 1)])
+def test_gemm_o4(m, n, k, flags):
+    from atom_b200 import ops
+    t = O.make_gemm_inputs(m, n, k, seed=m + n + k)
+    d, ds = ops.dense_layer_gemm_i4_o4(*[T(x) for x in t], flags=flags)
+    d, ds = d.cpu().numpy(), ds.cpu().numpy()
+    rows = None if m * n * k <= (1 << 28) else [0, 3, m - 1]
+    rd, rds = O.gemm_i4_o4(*t, rows=rows)
+    if rows is not None:
+        d, ds = d[rows], ds[rows]
+    assert np.array_equal(ds.view(np.uint16), rds.view(np.uint16))       # (scale, zero): bit exact
+    assert np.array_equal(d, rd)                                           # packed INT4: bit exact
+
+
+def _kv_fixture(rng, B, H, P, L, lens):
+    pages = sum((l + P - 1) // P for l in lens) + 3
+    data = rng.integers(0, 256, (pages, L, 2, H, P, 64), dtype=np.uint8)
+    param = np.stack([rng.uniform(0.01, 0.05, (pages, L, 2, H, P)), rng.uniform(0, 0.4, (pages, L, 2, H, P))], -1).astype(np.float16)
+    perm = rng.permutation(pages)
+    indptr, indices, last, c = [0], [], [], 0
+    for l in lens:
+        npg = (l + P - 1) // P
+        indices += list(perm[c:c + npg]); c += npg
+        indptr.append(len(indices)); last.append((l - 1) % P + 1)
+    return data, param, np.array(indptr, np.int32), np.array(indices, np.int32), np.array(last, np.int32)
+
+
+class _KV:
+    def __init__(self, data, param, indptr, indices, last):
+        self.data, self.param, self.indptr, self.indicies, self.last_page_offset = T(data), T(param), T(indptr), T(indices), T(last)
+
+
+@pytest.mark.parametrize("B,H,P,lens", [(3, 2, 16, [1, 37, 64]), (7, 4, 16, [5, 499, 16, 17, 250, 333, 32]),
+                                        (2, 3, 32, [2048, 777]), (4, 2, 8, [8, 9, 1, 100])])
+def test_batch_decode(B, H, P, lens):
+    from atom_b200 import ops
+    rng = np.random.default_rng(B * 100 + P)
+    L = 2
+    data, param, indptr, indices, last = _kv_fixture(rng, B, H, P, L, lens)
+    q = rng.standard_normal((B, H, 128)).astype(np.float16)
+    kv = _KV(data, param, indptr, indices, last)
+    for layer in range(L):
+        o = ops.batch_decode_i4(T(q), kv, layer).cpu().numpy()
+        ref = O.batch_decode_i4(q, data, param, indptr, indices, last, layer)
+        # FP16 output of an FP32 softmax-attention with approximate-vs-exact transcendental differences:
+        # rtol/atol 1e-3 (the reference intends 5e-4 against an FP16 torch pipeline, test_batch_decode_int4.py:9-14)
+        assert np.allclose(o.astype(np.float32), ref.astype(np.float32), rtol=1e-3, atol=1e-3)
+
+
+def test_append_and_init_kv_bit_exact():
+    from atom_b200 import ops
+    rng = np.random.default_rng(5)
+    B, H, P, L = 5, 8, 16, 3
+    lens = [1, 16, 17, 40, 64]
+    data, param, indptr, indices, last = _kv_fixture(rng, B, H, P, L, lens)
+    k = rng.integers(0, 256, (B, H, 64), dtype=np.uint8); v = rng.integers(0, 256, (B, H, 64), dtype=np.uint8)
+    kp = rng.random((B, H, 2)).astype(np.float16); vp = rng.random((B, H, 2)).astype(np.float16)
+    kv = _KV(data, param, indptr, indices, last)
+    ops.append_kv_i4(kv, T(k), T(v), T(kp), T(vp), 1)
+    d_ref, p_ref = data.copy(), param.copy()
+    O.append_kv_i4(d_ref, p_ref, indptr, indices, last, k, v, kp, vp, 1)
+    assert np.array_equal(kv.data.cpu().numpy(), d_ref) and np.array_equal(kv.param.cpu().numpy().view(np.uint16), p_ref.view(np.uint16))
+    tot = sum(lens)
+    K = rng.integers(0, 256, (tot, H, 64), dtype=np.uint8); V = rng.integers(0, 256, (tot, H, 64), dtype=np.uint8)
+    KP = rng.random((tot, H, 2)).astype(np.float16); VP = rng.random((tot, H, 2)).astype(np.float16)
+    sl = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    kv2 = _KV(data, param, indptr, indices, last)
+    ops.init_kv_i4(kv2, T(K), T(V), T(KP), T(VP), T(sl), 2)
+    d_ref, p_ref = data.copy(), param.copy()
+    O.init_kv_i4(d_ref, p_ref, indptr, indices, last, K, V, KP, VP, sl, 2)
+    assert np.array_equal(kv2.data.cpu().numpy(), d_ref) and np.array_equal(kv2.param.cpu().numpy().view(np.uint16), p_ref.view(np.uint16))
+
+
+def test_errors_are_loud():
+    from atom_b200 import ops
+    t = [T(x) for x in O.make_gemm_inputs(16, 100, 512)]   # N not a multiple of 8
+    with pytest.raises(RuntimeError):
+        ops.dense_layer_gemm_i4_fp16(*t)
+    with pytest.raises(RuntimeError):
+        ops.reorder_fp16_i4(torch.zeros(4, 4096, dtype=torch.float16), torch.zeros(4096, dtype=torch.int16))  # CPU tensors

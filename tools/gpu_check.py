@@ -1,0 +1,117 @@
+"""GPU-side diagnostics and timing (run under gpurun; writes JSON lines to stdout).
+
+  python tools/gpu_check.py diag            structured GEMM probes (localise layout / descriptor bugs)
+  python tools/gpu_check.py time [Ms...]    GEMM timing, ours (auto / tall / skinny) vs the reference kernel
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import oracle as O  # noqa: E402
+from oracle import ref_gpu as R  # noqa: E402
+from atom_b200 import ops  # noqa: E402
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ulp(a, b):
+    def key(x):
+        u = x.view(np.uint16).astype(np.int32)
+        return np.where(u & 0x8000, 0x8000 - u, u)
+    return np.abs(key(a) - key(b))
+
+
+def diag():
+    cases = [(16, 128, 256, 2), (16, 128, 256, 5), (128, 128, 512, 2), (16, 256, 4096, 5), (16, 256, 4096, 4), (200, 256, 1024, 2)]
+    for (m, n, k, flags) in cases:
+        for probe in ("ones", "int_only", "random"):
+            t = list(O.make_gemm_inputs(m, n, k, seed=7))
+            g = k // 128 - 1
+            if probe == "ones":
+                t[0] = O.pack_int4(np.ones((m, k - 128), np.int8)); t[1] = O.pack_int4(np.ones((n, k - 128), np.int8))
+                t[4] = np.ones((m, 128), np.int8); t[5] = np.ones((n, 128), np.int8)
+            if probe in ("ones", "int_only"):
+                t[2] = O.a_scale_to_layout(np.ones((g, m))); t[3] = np.ones((g, n), np.float16)
+                t[6] = O.a_scale_to_layout(np.ones((1, m)))[0]; t[7] = np.ones((n,), np.float16)
+                if probe == "int_only":   # keep magnitudes inside fp16
+                    t[2] = O.a_scale_to_layout(np.full((g, m), 2.0 ** -6)); t[6] = O.a_scale_to_layout(np.full((1, m), 2.0 ** -10))[0]
+            try:
+                d = ops.dense_layer_gemm_i4_fp16(*[T(x) for x in t], flags=flags)
+                torch.cuda.synchronize()
+                d = d.cpu().numpy()
+            except Exception as e:  # noqa: BLE001
+                print(json.dumps({"diag": [m, n, k, flags], "probe": probe, "error": str(e)[:300]}), flush=True)
+                continue
+            ref = O.gemm_i4_o16(*t)
+            u = ulp(d, ref)
+            rec = {"diag": [m, n, k, flags], "probe": probe, "max_ulp": int(u.max()), "mismatch_frac": float((u != 0).mean())}
+            if u.max() != 0:
+                bad = u != 0
+                rec["bad_rows"] = np.nonzero(bad.any(1))[0][:16].tolist()
+                rec["bad_cols"] = np.nonzero(bad.any(0))[0][:16].tolist()
+                rec["got_sample"] = d[:2, :8].astype(float).tolist()
+                rec["ref_sample"] = ref[:2, :8].astype(float).tolist()
+            print(json.dumps(rec), flush=True)
+
+
+def bench(fn, nrot, iters=50, warmup=5):
+    """CUDA-event timing on the current stream; `fn(i)` must use buffer set i % nrot (rotating sets defeat L2)."""
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(i); e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[len(ts) // 10], ts[(len(ts) * 9) // 10]
+
+
+def timing(ms_list):
+    n = k = 4096
+    for m in ms_list:
+        base = O.make_gemm_inputs(m, n, k, seed=1)
+        per_set = sum(x.nbytes for x in base)
+        nrot = max(3, int(300e6 // per_set) + 1)     # > 126 MB L2 in flight
+        sets = [[T(x) for x in base] for _ in range(nrot)]
+        outs = [torch.empty((m, n), dtype=torch.float16, device="cuda") for _ in range(nrot)]
+        ops_count = 2.0 * m * n * k
+        rec = {"time": [m, n, k], "rot_sets": nrot}
+        variants = {"auto": 0, "nosplit": 1, "tall": 2}
+        if m <= 128:
+            variants["skinny_nosplit"] = 5
+            variants["skinny"] = 4
+        for name, flags in variants.items():
+            try:
+                med, p10, p90 = bench(lambda i: ops.dense_layer_gemm_i4_fp16(*sets[i % nrot], flags=flags), nrot)
+                rec[name] = {"us": round(med, 2), "p10": round(p10, 2), "p90": round(p90, 2), "TOPS": round(ops_count / med * 1e-6, 1)}
+            except Exception as e:  # noqa: BLE001
+                rec[name] = {"error": str(e)[:200]}
+        if R.available():
+            med, p10, p90 = bench(lambda i: R.gemm_i4_o16(*sets[i % nrot], d=outs[i % nrot], sync=0), nrot)
+            rec["reference_kernel"] = {"us": round(med, 2), "TOPS": round(ops_count / med * 1e-6, 1)}
+        # launch-overhead-free estimate: many back-to-back launches inside one event pair
+        reps = 20
+        def burst(i):
+            for j in range(reps):
+                ops.dense_layer_gemm_i4_fp16(*sets[(i * reps + j) % nrot], flags=0)
+        med, _, _ = bench(burst, nrot, iters=10, warmup=2)
+        rec["auto_back_to_back_us"] = round(med / reps, 2)
+        print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1]
+    if cmd == "diag":
+        diag()
+    elif cmd == "time":
+        timing([int(x) for x in sys.argv[2:]] or [16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
