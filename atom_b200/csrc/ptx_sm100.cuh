@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace atom {
 
@@ -32,8 +33,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Spin on the phase parity.  A pipeline bug must not hang the GPU (and the box): after ~4 s of spinning the
+// thread reports which barrier it was waiting on and traps, turning a deadlock into a launch error.
+#ifndef ATOM_MBAR_TIMEOUT_CYCLES
+#define ATOM_MBAR_TIMEOUT_CYCLES (8000000000ll)
+#endif
+__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+  printf("atom_b200: mbarrier wait timed out: block (%d,%d,%d) thread %d smem 0x%x parity %u\n", blockIdx.x, blockIdx.y,
+         blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > ATOM_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
+  }
 }
 
 // ------------------------------------------------------------------ proxies / fences
