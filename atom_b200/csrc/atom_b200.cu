@@ -20,6 +20,7 @@
 namespace {
 
 thread_local std::string g_err;
+unsigned long long* g_trace = nullptr;   // atom_gemm_set_trace
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -156,7 +157,7 @@ int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t f
   const bool split = !(flags & ATOM_GEMM_NO_SPLITK) && groups >= 8 && ch_tiles * ((op.M + 63) / 64) < 120;
   if (op.M <= 16) return split ? launch_gemm<true, 16, 8, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 16, 8, 3, 1, kO4>(op, args, stream);
   if (op.M <= 32) return split ? launch_gemm<true, 32, 8, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 32, 8, 3, 1, kO4>(op, args, stream);
-  return split ? launch_gemm<true, 64, 6, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 64, 6, 3, 1, kO4>(op, args, stream);
+  return split ? launch_gemm<true, 64, 4, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 64, 6, 3, 1, kO4>(op, args, stream);
 }
 
 int gemm_common(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
@@ -176,7 +177,7 @@ int gemm_common(const void* a, const void* b, const void* a_scale, const void* b
   args.a_scale = (const __half*)a_scale; args.b_scale = (const __half*)b_scale;
   args.a_keeper_scale = (const __half*)a_keeper_scale; args.b_keeper_scale = (const __half*)b_keeper_scale;
   args.d = o4 ? nullptr : (__half*)d; args.d4 = o4 ? (uint8_t*)d : nullptr; args.d_scale = (__half2*)d_scale;
-  args.M = (int)M; args.N = (int)N; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M);
+  args.M = (int)M; args.N = (int)N; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M); args.trace = g_trace;
   return o4 ? gemm_dispatch<true>(op, args, flags, (cudaStream_t)stream) : gemm_dispatch<false>(op, args, flags, (cudaStream_t)stream);
 }
 
@@ -195,6 +196,7 @@ int atom_version(void) { return 100; }
 const char* atom_last_error(void) { return g_err.c_str(); }
 int atom_scale_index(int row) { return atom::scale_index(row); }
 int atom_scale_size(int rows) { return atom::scale_size(rows); }
+int atom_gemm_set_trace(void* device_buffer) { g_trace = (unsigned long long*)device_buffer; return ATOM_OK; }
 
 int atom_reorder_fp16_i4(const void* hidden, const void* reorder_index, int seq_len, int hidden_dim, void* o_outliers,
                          void* o_norms, void* outlier_scales, void* norm_scales, void* stream) {

@@ -33,7 +33,20 @@ struct GemmArgs {
   __half2* d_scale;              // o4 : [M][N/128] (scale, zero)
   int M, N, G;                   // G = number of INT4 groups = K/128 - 1
   int lda_scale;                 // S(M)
+  unsigned long long* trace;     // optional device buffer [ctas][128] of clock64 stamps (atom_gemm_set_trace), else null
 };
+
+// timeline stamps for pipeline debugging (tools/gpu_check.py trace): slot layout per CTA
+//   0 start | 1 setup done | 2 epilogue loop done | 3 reduction done | 4 end
+//   (first 16 iterations, 8 for the last row) 8+it producer issued | 24+it converter got its expanded slot |
+//   40+it converter saw the packed tile | 56+it conversion stored | 72+it converter fenced+arrived | 88+it MMA thread woke |
+//   104+it accumulator ready (epilogue saw tmem_full) | 120+it epilogue done
+__device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
+  if (a.trace != nullptr && slot < 128) {
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    a.trace[(size_t)cta * 128 + slot] = (unsigned long long)clock64();
+  }
+}
 
 __host__ __device__ __forceinline__ int scale_index(int row) { return (row / 16) * 64 + (row % 8) * 8 + ((row / 8) % 2); }
 __host__ __device__ __forceinline__ int scale_size(int m) { return m / 16 * 64 + 64 - (1 - (m % 16) / 8) * (8 - (m % 8)) * 8; }
@@ -43,25 +56,29 @@ struct GemmCfg {
   static constexpr int BM = 128;                                  // MMA M (TMEM lanes)
   static constexpr int NB = (BN <= 128) ? 4 : 2;                  // TMEM accumulator buffers
   static constexpr int TMEM_COLS = (NB * BN < 32) ? 32 : NB * BN; // power of two for BN in {16..256}
-  static constexpr int SCALE_SLOTS = kExp + NB + 1;               // see converter/epilogue lifetime argument
+  static constexpr int SCALE_SLOTS = 8;                           // scale ring depth (loader runs this far ahead)
+  static constexpr int SCALE_SLOT_BYTES = 512;                    // 256 B MMA-M side + 256 B MMA-N side, raw copies
   static constexpr int EPI_WGS = (BN >= 64) ? 2 : 1;              // epilogue warpgroups
   static constexpr int CPT = BN / EPI_WGS;                        // accumulator columns per epilogue thread
-  static constexpr int THREADS = 256 + 128 * EPI_WGS;
+  static constexpr int CONV_WARPS = kSwap ? 8 : 4;                // decode shapes are converter-latency bound: 2 warps / SMSP
+  static constexpr int CONV_THREADS = CONV_WARPS * 32;
+  static constexpr int THREADS = 256 + 128 * EPI_WGS + (CONV_WARPS - 4) * 32;   // extra converters sit after the epilogue
   static constexpr int PACK_P = BM * 64, PACK_Q = BN * 64;        // bytes per packed stage
   static constexpr int EXP_P = BM * 128, EXP_Q = BN * 128;        // bytes per expanded stage
   static constexpr int OFF_EXP_P = 0;
   static constexpr int OFF_EXP_Q = OFF_EXP_P + kExp * EXP_P;
   static constexpr int OFF_PACK_P = OFF_EXP_Q + kExp * ((EXP_Q + 1023) / 1024 * 1024);
   static constexpr int OFF_PACK_Q = OFF_PACK_P + kPack * PACK_P;
-  static constexpr int OFF_SM = OFF_PACK_Q + kPack * PACK_Q;      // half2 per MMA-M row per slot
-  static constexpr int OFF_SN = OFF_SM + SCALE_SLOTS * BM * 4;    // half per MMA-N column per slot
-  static constexpr int OFF_BAR = (OFF_SN + SCALE_SLOTS * BN * 2 + 15) / 16 * 16;
-  static constexpr int NUM_BARS = 2 * kPack + 2 * kExp + 2 * NB + SCALE_SLOTS;
+  static constexpr int OFF_SM = OFF_PACK_Q + kPack * PACK_Q;      // scale ring (16-B aligned)
+  static constexpr int RED_BYTES = BM * BN * 4;                   // one rank's split-K partial [col][row] fp32
+  static constexpr int OFF_RED = OFF_SM + SCALE_SLOTS * SCALE_SLOT_BYTES;   // leader only: (kSplit-1) pushed partials
+  static constexpr int OFF_BAR = OFF_RED + (kSplit > 1 ? (kSplit - 1) * RED_BYTES : 0);
+  static constexpr int NUM_BARS = 2 * kPack + 2 * kExp + 2 * NB + 2 * SCALE_SLOTS;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;     // + slack for the 1024-B alignment fix-up
-  static constexpr int RED_BYTES = BM * BN * 4;                   // split-K partials, aliased on the expanded ring
   static_assert(!kO4 || (BN == 128 || kSwap), "o4 (tall) quantises one 128-column head per CTA");
-  static_assert(kSplit == 1 || RED_BYTES <= OFF_SM, "split-K reduction buffer must fit in the tile rings");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(BN <= 128, "scale slot holds 128 channel scales");
   static_assert(NB * BN <= 512, "TMEM has 512 columns");
 };
 
@@ -75,18 +92,29 @@ __device__ __forceinline__ void expand_chunk(const uint4& w, uint4& lo, uint4& h
   lo.w = (w.w << 4) & 0xF0F0F0F0u; hi.w = w.w & 0xF0F0F0F0u;
 }
 
-// convert `rows` packed rows (64 B each, dense) into the K-major SWIZZLE_128B layout (128 B rows, 8-row atoms)
-template <int kRows>
+// convert `rows` packed rows (64 B each, dense) into the K-major SWIZZLE_128B layout (128 B rows, 8-row atoms).
+// All of a thread's 16-B chunks are loaded before any is expanded/stored so that the LDS latencies overlap.
+template <int kRows, int kThreads>
 __device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ packed, uint8_t* __restrict__ expanded, int t) {
+  constexpr int kChunks = kRows * 4;
+  constexpr int kIter = (kChunks + kThreads - 1) / kThreads;
+  uint4 w[kIter];
 #pragma unroll
-  for (int c = t; c < kRows * 4; c += 128) {
-    const int r = c >> 2, j = c & 3;
-    const uint4 w = *reinterpret_cast<const uint4*>(packed + c * 16);
-    uint4 lo, hi;
-    expand_chunk(w, lo, hi);
-    uint8_t* row = expanded + (r >> 3) * 1024 + (r & 7) * 128;
-    *reinterpret_cast<uint4*>(row + (((2 * j) ^ (r & 7)) << 4)) = lo;
-    *reinterpret_cast<uint4*>(row + (((2 * j + 1) ^ (r & 7)) << 4)) = hi;
+  for (int i = 0; i < kIter; ++i) {
+    const int c = t + i * kThreads;
+    if (kChunks % kThreads == 0 || c < kChunks) w[i] = *reinterpret_cast<const uint4*>(packed + c * 16);
+  }
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const int c = t + i * kThreads;
+    if (kChunks % kThreads == 0 || c < kChunks) {
+      const int r = c >> 2, j = c & 3;
+      uint4 lo, hi;
+      expand_chunk(w[i], lo, hi);
+      uint8_t* row = expanded + (r >> 3) * 1024 + (r & 7) * 128;
+      *reinterpret_cast<uint4*>(row + (((2 * j) ^ (r & 7)) << 4)) = lo;
+      *reinterpret_cast<uint4*>(row + (((2 * j + 1) ^ (r & 7)) << 4)) = hi;
+    }
   }
 }
 
@@ -98,8 +126,10 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
                const __grid_constant__ CUtensorMap tm_q8,   // INT8 keeper, MMA-N operand  (box 128 B x BN rows, SW128)
                const GemmArgs args) {
   using C = GemmCfg<kSwap, BN, kPack, kExp, kSplit, kO4>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-B alignment (SWIZZLE_128B atoms) by offsetting the shared array, NOT by integer-casting the pointer:
+  // an integer round trip makes the compiler fall back to generic LD/ST for every smem access.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* pack_full = bars;
@@ -109,6 +139,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
   uint64_t* tmem_full = exp_empty + kExp;
   uint64_t* tmem_empty = tmem_full + C::NB;
   uint64_t* scale_full = tmem_empty + C::NB;
+  uint64_t* scale_empty = scale_full + C::SCALE_SLOTS;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,29 +161,40 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
     g_end = min(g_begin + per, total_groups);
   }
   const int iters = g_end - g_begin;
+  if (threadIdx.x == 0) trace_stamp(args, 0);
 
   // ---------------------------------------------------------------- one-time setup
+  // Thread 0 initialises the barriers and immediately fires the first kPack stages of TMA loads: the DRAM round trip
+  // of the first tiles (the longest latency on the critical path of a decode-sized problem) then overlaps the TMEM
+  // allocation and the CTA-wide sync instead of following them.
+  int itp_issued = 0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_p4); tma_prefetch_desc(&tm_q4); tma_prefetch_desc(&tm_p8); tma_prefetch_desc(&tm_q8);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kPack; ++i) { mbar_init(&pack_full[i], 1); mbar_init(&pack_empty[i], 4); }
-    for (int i = 0; i < kExp; ++i) { mbar_init(&exp_full[i], 4); mbar_init(&exp_empty[i], 1); }
+    for (int i = 0; i < kPack; ++i) { mbar_init(&pack_full[i], 1); mbar_init(&pack_empty[i], C::CONV_WARPS); }
+    for (int i = 0; i < kExp; ++i) { mbar_init(&exp_full[i], C::CONV_WARPS); mbar_init(&exp_empty[i], 1); }
     for (int i = 0; i < C::NB; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * C::EPI_WGS); }
-    for (int i = 0; i < C::SCALE_SLOTS; ++i) mbar_init(&scale_full[i], 4);
+    for (int i = 0; i < C::SCALE_SLOTS; ++i) { mbar_init(&scale_full[i], 32); mbar_init(&scale_empty[i], 4 * C::EPI_WGS); }
     fence_barrier_init();
+    for (; itp_issued < kPack && itp_issued < iters && g_begin + itp_issued < args.G; ++itp_issued) {
+      const int g = g_begin + itp_issued;
+      mbar_arrive_expect_tx(&pack_full[itp_issued], C::PACK_P + C::PACK_Q);
+      tma_load_2d(smem + C::OFF_PACK_P + itp_issued * C::PACK_P, &tm_p4, &pack_full[itp_issued], g * 64, p0);
+      tma_load_2d(smem + C::OFF_PACK_Q + itp_issued * C::PACK_Q, &tm_q4, &pack_full[itp_issued], g * 64, q0);
+      if (itp_issued < 16) trace_stamp(args, 8 + itp_issued);
+    }
   }
   if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) trace_stamp(args, 1);
 
   if (warp == 0) {
     // ============================================================ TMA producer (INT4 groups only)
     if (lane == 0) {
-      int itp = 0;
-      for (int it = 0; it < iters; ++it) {
+      int itp = itp_issued;
+      for (int it = itp_issued; it < iters; ++it) {
         const int g = g_begin + it;
         if (g >= args.G) break;  // keeper is loaded by the converter straight into the expanded ring
         const int s = itp % kPack;
@@ -160,6 +202,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
         mbar_arrive_expect_tx(&pack_full[s], C::PACK_P + C::PACK_Q);
         tma_load_2d(smem + C::OFF_PACK_P + s * C::PACK_P, &tm_p4, &pack_full[s], g * 64, p0);
         tma_load_2d(smem + C::OFF_PACK_Q + s * C::PACK_Q, &tm_q4, &pack_full[s], g * 64, q0);
+        if (it < 16) trace_stamp(args, 8 + it);
         ++itp;
       }
     }
@@ -172,6 +215,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
         mbar_wait(&tmem_empty[b], ((it / C::NB) & 1) ^ 1);
         mbar_wait(&exp_full[e], (it / kExp) & 1);
         tc_fence_after();
+        if (it < 16) trace_stamp(args, 88 + it);
         const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_P + e * C::EXP_P));
         const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + e * ((C::EXP_Q + 1023) / 1024 * 1024)));
 #pragma unroll
@@ -181,46 +225,61 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
         umma_commit(&tmem_full[b]);   // accumulator of this group is complete
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ============================================================ converter warpgroup
-    const int t = threadIdx.x - 128;
+  } else if (warp == 3) {
+    // ============================================================ scale loader: cp.async straight into the scale ring,
+    // completion counted on scale_full by the copy engine -- no thread ever waits on a scale's DRAM latency.
+    // Slot layout (raw copies of the reference layouts):
+    //   [0,256)   MMA-M side: tall  -> 64 (lower,upper) half2 words of the A-scale rows   (word = (r/16)*8 + r%8)
+    //                          skinny-> 128 B-scale halves of the channel tile (thread n reads the pair word n/2)
+    //   [256,512) MMA-N side: tall  -> BN B-scale halves;  skinny -> BN/16*8 (lower,upper) words of the token rows
+    for (int it = 0; it < iters; ++it) {
+      const int g = g_begin + it;
+      const bool keeper = (g == args.G);
+      const int slot = it % C::SCALE_SLOTS;
+      mbar_wait(&scale_empty[slot], ((it / C::SCALE_SLOTS) & 1) ^ 1);
+      const __half* as_row = keeper ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
+      const __half* bs_row = keeper ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
+      uint8_t* slot_p = smem + C::OFF_SM + slot * C::SCALE_SLOT_BYTES;
+      constexpr int TOK = kSwap ? BN : C::BM, CHN = kSwap ? C::BM : BN;
+      uint8_t* tok_dst = slot_p + (kSwap ? 256 : 0);
+      uint8_t* chn_dst = slot_p + (kSwap ? 0 : 256);
+#pragma unroll
+      for (int w = lane; w < TOK / 2; w += 32) {              // A-scale words: rows (16 blk + i, 16 blk + i + 8)
+        const int blk = w >> 3, i = w & 7;
+        if (m0 + 16 * blk + i < args.M) cp_async_4(tok_dst + w * 4, as_row + 64 * (m0 / 16 + blk) + 8 * i);
+      }
+#pragma unroll
+      for (int c = lane; c < CHN / 8; c += 32)                // B-scale: 8 channels per 16-B chunk
+        if (n0 + 8 * c < args.N) cp_async_16(chn_dst + c * 16, bs_row + n0 + 8 * c);
+      cp_async_mbar_arrive_noinc(&scale_full[slot]);
+    }
+  } else if ((warp >= 4 && warp < 8) || warp >= 8 + 4 * C::EPI_WGS) {
+    // ============================================================ converter warps (4, or 8 for decode shapes)
+    const int t = (warp < 8 ? warp - 4 : warp - 8 - 4 * C::EPI_WGS + 4) * 32 + lane;
     int itp = 0;
     for (int it = 0; it < iters; ++it) {
       const int g = g_begin + it;
       const bool keeper = (g == args.G);
-      // scales of this group, fetched early so that their latency hides behind the barrier waits
-      const __half* as_row = keeper ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
-      const __half* bs_row = keeper ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
-      __half2 sm_val = __half2half2(__ushort_as_half(0));
-      __half sn_val = __ushort_as_half(0);
-      if constexpr (!kSwap) {
-        if (m0 + t < args.M) sm_val = __half2half2(as_row[scale_index(m0 + t)]);
-        if (t < BN && n0 + t < args.N) sn_val = bs_row[n0 + t];
-      } else {
-        const int n = n0 + t;   // reference column pairing: rows m%16<8 use sB[n&~1], others sB[n|1]
-        if (n < args.N) sm_val = __halves2half2(bs_row[n & ~1], bs_row[min(n | 1, args.N - 1)]);
-        if (t < BN && m0 + t < args.M) sn_val = as_row[scale_index(m0 + t)];
-      }
       const int e = it % kExp;
       uint8_t* exp_p = smem + C::OFF_EXP_P + e * C::EXP_P;
       uint8_t* exp_q = smem + C::OFF_EXP_Q + e * ((C::EXP_Q + 1023) / 1024 * 1024);
       mbar_wait(&exp_empty[e], ((it / kExp) & 1) ^ 1);
-      const int slot = it % C::SCALE_SLOTS;
-      reinterpret_cast<__half2*>(smem + C::OFF_SM)[slot * C::BM + t] = sm_val;
-      if (t < BN) reinterpret_cast<__half*>(smem + C::OFF_SN)[slot * BN + t] = sn_val;
+      if (t == 0 && it < 16) trace_stamp(args, 24 + it);
       if (!keeper) {
         const int s = itp % kPack;
         mbar_wait(&pack_full[s], (itp / kPack) & 1);
-        convert_tile<C::BM>(smem + C::OFF_PACK_P + s * C::PACK_P, exp_p, t);
-        convert_tile<BN>(smem + C::OFF_PACK_Q + s * C::PACK_Q, exp_q, t);
+        if (t == 0 && it < 16) trace_stamp(args, 40 + it);
+        convert_tile<C::BM, C::CONV_THREADS>(smem + C::OFF_PACK_P + s * C::PACK_P, exp_p, t);
+        convert_tile<BN, C::CONV_THREADS>(smem + C::OFF_PACK_Q + s * C::PACK_Q, exp_q, t);
+        if (t == 0 && it < 16) trace_stamp(args, 56 + it);
         fence_proxy_async_smem();     // generic-proxy stores -> visible to tcgen05.mma operand fetch
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&pack_empty[s]); mbar_arrive(&scale_full[slot]); mbar_arrive(&exp_full[e]); }
+        if (lane == 0) { mbar_arrive(&pack_empty[s]); mbar_arrive(&exp_full[e]); }
+        if (t == 0 && it < 16) trace_stamp(args, 72 + it);
         ++itp;
       } else {
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&scale_full[slot]);
           if (t == 0) {
             mbar_arrive_expect_tx(&exp_full[e], C::EXP_P + C::EXP_Q);
             tma_load_2d(exp_p, &tm_p8, &exp_full[e], 0, p0);
@@ -231,7 +290,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 8 + 4 * C::EPI_WGS) {
     // ============================================================ epilogue warpgroup(s)
     const int wq = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = wq * 32 + lane;                // MMA-M row == TMEM lane
@@ -246,10 +305,23 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
       const bool keeper = (g == args.G);
       const int slot = it % C::SCALE_SLOTS, b = it % C::NB;
       mbar_wait(&scale_full[slot], (it / C::SCALE_SLOTS) & 1);
-      const __half2 sm2 = reinterpret_cast<const __half2*>(smem + C::OFF_SM)[slot * C::BM + row];
-      const __half* sn = reinterpret_cast<const __half*>(smem + C::OFF_SN) + slot * BN + colbase;
+      const uint8_t* slot_p = smem + C::OFF_SM + slot * C::SCALE_SLOT_BYTES;
+      __half2 sm2;
+      const __half* sn;      // tall: B-scale halves of this thread's columns
+      const __half2* snw;    // skinny: (lower, upper) A-scale words of this thread's token columns
+      if constexpr (!kSwap) {
+        const __half2 pw = reinterpret_cast<const __half2*>(slot_p)[(row >> 4) * 8 + (row & 7)];
+        sm2 = __half2half2(upper ? __high2half(pw) : __low2half(pw));
+        sn = reinterpret_cast<const __half*>(slot_p + 256) + colbase;
+        snw = nullptr;
+      } else {
+        sm2 = reinterpret_cast<const __half2*>(slot_p)[row >> 1];     // {sB[n&~1], sB[n|1]}
+        sn = nullptr;
+        snw = reinterpret_cast<const __half2*>(slot_p + 256) + (colbase >> 4) * 8;
+      }
       mbar_wait(&tmem_full[b], (it / C::NB) & 1);
       tc_fence_after();
+      if (warp == 8 && lane == 0 && it < 16) trace_stamp(args, 104 + it);
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * BN + colbase);
       constexpr int CH = (C::CPT >= 32) ? 32 : 16;
 #pragma unroll
@@ -288,7 +360,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
           for (int j = 0; j < CH; j += 16) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const __half2 a2 = __halves2half2(sn[c0 + j + i], sn[c0 + j + i + 8]);
+              const __half2 a2 = snw[((c0 + j) >> 4) * 8 + i];      // (sA[token j+i], sA[token j+i+8])
               const float2 rs = __half22float2(__hmul2(a2, sm2));
               acc[c0 + j + i] = fmaf((float)(int32_t)r[j + i], rs.x, acc[c0 + j + i]);
               acc[c0 + j + i + 8] = fmaf((float)(int32_t)r[j + i + 8], rs.y, acc[c0 + j + i + 8]);
@@ -296,27 +368,32 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&scale_empty[slot]);       // this warp no longer reads the slot
+      if (warp == 8 && lane == 0 && it < 8) trace_stamp(args, 120 + it);
     }
+    if (warp == 8 && lane == 0) trace_stamp(args, 2);
 
-    // ------------------------------------------------------------ split-K: publish partials in smem
+    // ------------------------------------------------------------ split-K: push partials into the leader's smem
+    // Remote stores need no round trip (a pull would put several DSMEM read latencies on the critical path); one
+    // cluster barrier (release / acquire) publishes them, then only the leader goes on.
     if constexpr (kSplit > 1) {
-      float* red = reinterpret_cast<float*>(smem);   // [col][row], aliases the (now idle) expanded ring
+      if (krank != 0) {
+        const uint32_t remote = mapa_shared(smem_u32(smem + C::OFF_RED), 0) + (krank - 1) * C::RED_BYTES;
 #pragma unroll
-      for (int i = 0; i < C::CPT; ++i) red[(colbase + i) * C::BM + row] = acc[i];
-    }
-    if constexpr (kSplit > 1) {
+        for (int i = 0; i < C::CPT; ++i) st_dsmem_f32(remote + ((colbase + i) * C::BM + row) * 4, acc[i]);
+      }
       cluster_arrive(); cluster_wait();
       if (krank == 0) {
-        const uint32_t red_local = smem_u32(smem);
-#pragma unroll 1
-        for (uint32_t rk = 1; rk < (uint32_t)kSplit; ++rk) {
-          const uint32_t remote = mapa_shared(red_local, rk);
+        const float* red = reinterpret_cast<const float*>(smem + C::OFF_RED);
 #pragma unroll
-          for (int i = 0; i < C::CPT; ++i) acc[i] += ld_dsmem_f32(remote + ((colbase + i) * C::BM + row) * 4);
+        for (int rk = 0; rk < kSplit - 1; ++rk) {
+#pragma unroll
+          for (int i = 0; i < C::CPT; ++i) acc[i] += red[rk * (C::RED_BYTES / 4) + (colbase + i) * C::BM + row];
         }
       }
     }
-
+    if (warp == 8 && lane == 0) trace_stamp(args, 3);
     // ------------------------------------------------------------ output
     if (kSplit == 1 || krank == 0) {
       constexpr float kInv = 1.0f / 256.0f;   // exact: removes the 16*16 operand factor
@@ -416,12 +493,12 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
 
   // ---------------------------------------------------------------- teardown
   if constexpr (kSplit > 1) {
-    if (warp < 8) { cluster_arrive(); cluster_wait(); }   // pairs with the epilogue's first cluster barrier
-    cluster_arrive(); cluster_wait();                     // nobody exits while its smem may still be read remotely
+    if (!(warp >= 8 && warp < 8 + 4 * C::EPI_WGS)) { cluster_arrive(); cluster_wait(); }   // pairs with the epilogue's barrier
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  if (threadIdx.x == 0) trace_stamp(args, 4);
 }
 
 }  // namespace atom

@@ -79,6 +79,10 @@ ATOM_API int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, 
                     const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d,
                     void* d_scale, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream);
 
+/* Debug aid (no reference counterpart): when non-NULL, every GEMM CTA writes 128 clock64() stamps of its pipeline
+ * stages to device_buffer[cta*128 ...] (layout in gemm_i4_sm100.cuh).  NULL switches tracing off. */
+ATOM_API int atom_gemm_set_trace(void* device_buffer);
+
 /* replaces batch_decode_i4 (punica_ops.cc:82-120 -> FlashInferBatchDecodeKernel_i4<128>, flashinfer_impl.cuh:9-46)
  *   o,q f16 [B,H,128]  kv_data u8 [pages,L,2,H,P,64]  kv_param f16 [pages,L,2,H,P,2]
  *   kv_indptr i32 [B+1]  kv_indices i32 [nnz]  last_page_offset i32 [B] */

@@ -14,8 +14,8 @@ using namespace atom;
 // ------------------------------------------------------------------ (1) UTCIMMA peak
 template <int BN>
 __global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, unsigned long long* cycles) {
-  extern __shared__ uint8_t raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
   __shared__ uint32_t tptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
