@@ -299,6 +299,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
 #pragma unroll
     for (int i = 0; i < C::CPT; ++i) acc[i] = 0.f;
     const bool upper = kSwap ? false : (((m0 + row) & 15) >= 8);
+    const uint32_t pair_sel = upper ? 0x7632u : 0x5410u;   // one PRMT picks the odd (upper rows) or even channel of two pairs
 
     for (int it = 0; it < iters; ++it) {
       const int g = g_begin + it;
@@ -345,8 +346,8 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
           for (int p = 0; p < CH / 2; p += 2) {
             const __half2 n01 = *reinterpret_cast<const __half2*>(sn + c0 + 2 * p);
             const __half2 n23 = *reinterpret_cast<const __half2*>(sn + c0 + 2 * p + 2);
-            const __half2 sel = upper ? __halves2half2(__high2half(n01), __high2half(n23))
-                                      : __halves2half2(__low2half(n01), __low2half(n23));
+            const uint32_t selw = __byte_perm(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23), pair_sel);
+            const __half2 sel = *reinterpret_cast<const __half2*>(&selw);   // {sB[pair p], sB[pair p+1]} for this row's half
             const float2 rs = __half22float2(__hmul2(sm2, sel));
             acc[c0 + 2 * p + 0] = fmaf((float)(int32_t)r[2 * p + 0], rs.x, acc[c0 + 2 * p + 0]);
             acc[c0 + 2 * p + 1] = fmaf((float)(int32_t)r[2 * p + 1], rs.x, acc[c0 + 2 * p + 1]);

@@ -22,19 +22,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~the hint elapses)
+// instead of burning issue slots in a software spin loop.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
-// Spin on the phase parity.  A pipeline bug must not hang the GPU (and the box): after ~4 s of spinning the
-// thread reports which barrier it was waiting on and traps, turning a deadlock into a launch error.
+// A pipeline bug must not hang the GPU (and the box): after ~4 s the waiting thread reports the barrier and traps,
+// turning a deadlock into a launch error.  The clock is only consulted every 64 unsuccessful probes.
 #ifndef ATOM_MBAR_TIMEOUT_CYCLES
 #define ATOM_MBAR_TIMEOUT_CYCLES (8000000000ll)
 #endif
@@ -45,9 +47,14 @@ __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > ATOM_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
+    if ((++spins & 63u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > ATOM_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
+    }
   }
 }
 

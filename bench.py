@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline benchmark (BASELINE.json configs[1]): gemm_i4_o16, M=16, N=K=4096,
+group 128, INT8 keeper 128, on synthetic random-quantised operands.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--m M]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input: `gemms_per_step` independent GEMM problems
+(distinct operand sets, together larger than the 126 MB L2, so every launch streams its weights from HBM), launched
+back to back from one CUDA graph.  `value` = whole-job TOP/s with operands resident in HBM (OP = 2*M*N*K, the
+reference's convention, bench_dense_layer_gemm_i4_o16.cu:40-42); multi-GPU runs give every rank its own batch (weak
+scaling, no data-path collective: GEMM problems are independent units).  `e2e` = the same metric through the public
+operator (atom_b200.ops.dense_layer_gemm_i4_fp16) with HOST activations: per step one pinned H2D copy of the quantised
+activation tuple, the GEMM, and a D2H read of the FP16 result.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L2_BYTES = 126e6
+
+
+def algorithmic_bytes(m, n, k):
+    """packed operands + keepers + scales + FP16 output, per launch."""
+    g1 = k // 128
+    s_m = m // 16 * 64 + 64 - (1 - (m % 16) // 8) * (8 - (m % 8)) * 8
+    return (m + n) * (k - 128) // 2 + (m + n) * 128 + 2 * g1 * s_m + 2 * g1 * n + 2 * m * n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = [n for i, n in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap"))
+                   if any(r[i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows if r[3] not in ("[N/A]", ""))}
+
+
+def cpu_baseline(m, n, k, budget_s=12.0):
+    """The reference's simulated-quantisation CPU path (model/quant.py + qLinearLayer, BASELINE config #1), restated in
+    oracle/fakequant.py, timed on all host cores: quantise the weight once (untimed), then act fake-quant + F.linear."""
+    from oracle import fakequant as FQ   # the one other place bench.py may execute oracle/
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args = FQ.w4a4_args()
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(k, n, bias=False)
+    wq = FQ.fq_linear_weight(lin.weight.detach().float(), args)
+    x = torch.randn(m, k)
+    FQ.fq_linear_forward(x, wq, args)
+    t0, it = time.perf_counter(), 0
+    while True:
+        FQ.fq_linear_forward(x, wq, args)
+        it += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or it >= 200:
+            break
+    tops = 2.0 * m * n * k * it / el * 1e-12
+    return {"value": tops, "unit": "TOP/s", "cores": cores, "kind": "port",
+            "sample": f"{it} forwards of the fake-quant W4A4 linear (fp32 torch, act quant + F.linear) at M={m}, N={n}, K={k} in {el:.1f} s"}
+
+
+def ncu_traffic(m):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        return json.load(open(p)).get(f"gemm_m{m}", {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    M, N, K = a.m, 4096, 4096
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: atom_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ref_mode = a.impl == "reference"
+    if ref_mode:
+        from oracle import ref_gpu as R
+        if not R.available():
+            # no compiled reference on this box: time the CPU port instead (rank 0 only)
+            if rank == 0:
+                cb = cpu_baseline(M, N, K, budget_s=20.0)
+                print(json.dumps({"impl": "reference", "metric": "gemm_i4_o16_throughput", "value": cb["value"], "unit": "TOP/s",
+                                  "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True,
+                                  "config": {"workload": f"gemm_i4_o16 M={M} N={N} K={K} group128 keeper128"}, "cpu_baseline": cb,
+                                  "e2e": {"value": cb["value"], "unit": "TOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return
+    from atom_b200 import ops, synth
+
+    # ------------------------------------------------------------------ operands: R distinct sets > L2
+    one = synth.gemm_operands(M, N, K, dev, seed=1234 + rank)
+    per_set = sum(t.numel() * t.element_size() for t in one)
+    R_sets = int(2.4 * L2_BYTES // per_set) + 1
+    sets = [one] + [tuple(t.clone() for t in one) for _ in range(R_sets - 1)]
+    outs = [torch.empty((M, N), dtype=torch.float16, device=dev) for _ in range(R_sets)]
+    op_count = 2.0 * M * N * K
+    stream = torch.cuda.Stream(dev)
+
+    def run_batch():
+        if ref_mode:   # the reference launches on the legacy default stream (GEMM.cuh:763): not capturable, plain loop
+            for i in range(R_sets):
+                R.gemm_i4_o16(*sets[i], d=outs[i], sync=0)
+        else:
+            for i in range(R_sets):
+                ops.dense_layer_gemm_i4_fp16(*sets[i])
+
+    graph = None
+    with torch.cuda.stream(stream):
+        run_batch()
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if not ref_mode:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                run_batch()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            run_batch()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    with torch.cuda.stream(stream):
+        for _ in range(max(a.warmup, 3)):
+            step()
+        barrier()
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(a.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    ms_per_step = ms / a.steps
+    value = op_count * R_sets * world / (ms_per_step * 1e-3) * 1e-12
+
+    # ------------------------------------------------------------------ e2e: host activations in, host result out
+    act_bytes = sum(one[i].numel() * one[i].element_size() for i in (0, 2, 4, 6))
+    host_in = torch.empty(act_bytes + 64, dtype=torch.uint8).pin_memory()
+    host_out = torch.empty((M, N), dtype=torch.float16).pin_memory()
+    dev_in = torch.empty(act_bytes + 64, dtype=torch.uint8, device=dev)
+    views, off = [], 0
+    for i in (0, 2, 4, 6):   # a, a_scale, a_keeper, a_keeper_scale packed into one staging buffer (16-B aligned views)
+        nb = one[i].numel() * one[i].element_size()
+        host_in[off:off + nb] = one[i].reshape(-1).view(torch.uint8).cpu()
+        views.append(dev_in[off:off + nb].view(one[i].dtype).view(one[i].shape))
+        off += (nb + 15) // 16 * 16
+    e2e_steps = min(a.steps, 200) if ref_mode else a.steps
+
+    def e2e_step(i):
+        w = sets[i % R_sets]
+        dev_in.copy_(host_in, non_blocking=True)
+        if ref_mode:
+            torch.cuda.current_stream().synchronize()      # the reference kernel runs on the legacy stream
+            d = R.gemm_i4_o16(views[0], w[1], views[1], w[3], views[2], w[5], views[3], w[7], d=outs[i % R_sets], sync=1)
+        else:
+            d = ops.dense_layer_gemm_i4_fp16(views[0], w[1], views[1], w[3], views[2], w[5], views[3], w[7])
+        host_out.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the result
+
+    for i in range(5):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_tops = op_count * e2e_steps * world / t.item() * 1e-12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    us_per_launch = ms_per_step * 1e3 / R_sets
+    alg = algorithmic_bytes(M, N, K)
+    # HBM-bound up to the crossover M*~200; tensor-bound above it
+    int8_peak_tops = 2.0 * peaks.get("bf16_tflops", 1590.0)
+    t_hbm, t_tc = alg / (hbm_peak * 1e9), op_count / (int8_peak_tops * 1e12)
+    if t_hbm >= t_tc:
+        ach = alg / (us_per_launch * 1e-6) * 1e-9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic(M),
+                "algorithmic_bytes_per_launch": alg, "us_per_launch": us_per_launch, "peak_source": peak_src}
+    else:
+        ach = op_count / (us_per_launch * 1e-6) * 1e-12
+        roof = {"bound": "tensor", "achieved": ach, "peak": int8_peak_tops, "unit": "TOP/s", "frac": ach / int8_peak_tops,
+                "traffic": ncu_traffic(M), "us_per_launch": us_per_launch,
+                "peak_source": "2 x measured bf16 cuBLAS burst (INT8 tcgen05 = 2x bf16 rate; Blackwell has no INT4 MMA)"}
+    line = {
+        "metric": "gemm_i4_o16_throughput", "value": value, "unit": "TOP/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s4 x s4 -> s32 (via tcgen05 kind::i8), fp16 out",
+        "data": "synthetic", "impl": a.impl,
+        "config": {"workload": f"gemm_i4_o16 M={M} N={N} K={K} (K incl. 128 INT8 keeper) group_size=128", "gemms_per_step": R_sets,
+                   "l2": f"{R_sets} distinct operand sets per step = {R_sets * per_set / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
+                   "launch": "one CUDA graph replay per step" if graph is not None else "python loop on the legacy stream (reference launcher)",
+                   "parallelism": f"dp{world} (independent GEMM problems per rank, no collective)"},
+        "e2e": {"value": e2e_tops, "unit": "TOP/s", "h2d_bytes_per_step": act_bytes, "d2h_bytes_per_step": M * N * 2,
+                "steps": e2e_steps, "note": "one GEMM per step: pinned H2D of the activation tuple, op, D2H of D, stream sync"},
+        "gpu_launches": a.steps * R_sets + e2e_steps + 5,
+        "roofline": roof, "clocks": clocks,
+    }
+    if ref_mode:
+        line["cpu_baseline"] = {"value": value, "unit": "TOP/s", "cores": 0, "kind": "reference",
+                                "sample": "the reference's own CUDA kernel (oracle/_ref, compiled unmodified for sm_100a) on this GPU; "
+                                          "its CPU path is the fake-quant simulator, see cpu_baseline of the main arm"}
+        line["gpu_launches"] = 0   # none of OUR kernels ran in this arm
+    elif world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(M, N, K)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
