@@ -216,10 +216,11 @@ int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, cons
                          void* stream) {
   int rc = quant_check("rmsnorm_fp16_i4", seq_len, hidden_dim, o_outliers, o_norms, outlier_scales, norm_scales);
   if (rc) return rc;
-  ATOM_REQUIRE(hidden && weight && reorder_index && aligned16(hidden), "rmsnorm_fp16_i4: null or misaligned input");
+  ATOM_REQUIRE(hidden && weight && reorder_index && aligned16(hidden) && aligned16(weight), "rmsnorm_fp16_i4: null or misaligned input");
+  ATOM_REQUIRE(hidden_dim <= 32768, "rmsnorm_fp16_i4: hidden_dim=%d > 32768 unsupported", hidden_dim);
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(atom::rmsnorm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 512); attr_set = true; }
-  atom::rmsnorm_quant_kernel<<<seq_len, 128, (size_t)hidden_dim * 2 + 512, (cudaStream_t)stream>>>(
+  if (!attr_set) { cudaFuncSetAttribute(atom::rmsnorm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 * 2 / 2 + 65536 + 512); attr_set = true; }
+  atom::rmsnorm_quant_kernel<<<seq_len, 128, (size_t)hidden_dim * 4 + 512, (cudaStream_t)stream>>>(
       (const __half*)hidden, (const __half*)weight, eps, (const int16_t*)reorder_index, seq_len, hidden_dim,
       (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
   return check_launch("rmsnorm_fp16_i4");
@@ -266,12 +267,14 @@ int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, const void
                     num_heads, page_size, batch_size);
   if (rc) return rc;
   ATOM_REQUIRE(o && q, "batch_decode_i4: null q/o");
-  ATOM_REQUIRE(page_size <= 128, "batch_decode_i4: page_size=%d > 128 unsupported", page_size);
+  ATOM_REQUIRE(page_size % 8 == 0 && page_size <= 64, "batch_decode_i4: page_size=%d must be a multiple of 8, at most 64", page_size);
+  ATOM_REQUIRE(aligned16(kv_data) && aligned16(kv_param), "batch_decode_i4: KV pool must be 16-byte aligned");
   atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
                   (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
-  const size_t smem = (size_t)page_size * 64 * 8 + 64 * 8 + 4 * 4 * 34 * 4;
+  const size_t smem = (size_t)atom::DEC_STAGES * (136 * page_size) + (size_t)page_size * 64 * 8 + 64 * 8 + 4 * 4 * 34 * 4 +
+                      2 * atom::DEC_STAGES * 8 + 128;
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(atom::batch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 64 * 8 + 4096); attr_set = true; }
+  if (!attr_set) { cudaFuncSetAttribute(atom::batch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 136 * 64 + 64 * 64 * 8 + 8192); attr_set = true; }
   atom::batch_decode_kernel<<<dim3(batch_size, num_heads), atom::DEC_THREADS, smem, (cudaStream_t)stream>>>(
       (__half*)o, (const __half*)q, kv);
   return check_launch("batch_decode_i4");

@@ -56,12 +56,14 @@ reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ i
   extern __shared__ __align__(16) uint8_t smem_q[];
   __half* xs = reinterpret_cast<__half*>(smem_q);
   const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ng = hidden / 128;
+  short4 id_next = (warp < ng) ? *reinterpret_cast<const short4*>(idx + warp * 128 + lane * 4) : make_short4(0, 0, 0, 0);
   const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * hidden);
   for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) reinterpret_cast<uint4*>(xs)[i] = ld_nc_v4(src + i);
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ng = hidden / 128;
   for (int g = warp; g < ng; g += 8) {
-    const short4 id = *reinterpret_cast<const short4*>(idx + g * 128 + lane * 4);
+    const short4 id = id_next;
+    if (g + 8 < ng) id_next = *reinterpret_cast<const short4*>(idx + (g + 8) * 128 + lane * 4);
     float v[4] = {__half2float(xs[(uint16_t)id.x]), __half2float(xs[(uint16_t)id.y]), __half2float(xs[(uint16_t)id.z]),
                   __half2float(xs[(uint16_t)id.w])};
     quant_group_store(v, lane, row, g, ng, scale_ldm, s8out, s4out, s8scale, s4scale, hidden);
@@ -78,10 +80,15 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
                      __half* __restrict__ s8scale, __half* __restrict__ s4scale, int scale_ldm) {
   extern __shared__ __align__(16) uint8_t smem_q[];
   __half* xs = reinterpret_cast<__half*>(smem_q);
-  float* red = reinterpret_cast<float*>(smem_q + (size_t)hidden * 2);
+  __half* ws = xs + hidden;                             // norm weight staged too: the gather then never touches global
+  float* red = reinterpret_cast<float*>(smem_q + (size_t)hidden * 4);
   const int row = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, ng = hidden / 128;
   const int ept = hidden / 128;                       // contiguous elements per thread (multiple of 8 when hidden%1024==0)
   const __half* xr = x + (size_t)row * hidden;
+  // independent loads first: the first group's reorder indices and the weight row travel while the row is reduced
+  short4 id_next = (warp < ng) ? *reinterpret_cast<const short4*>(idx + warp * 128 + lane * 4) : make_short4(0, 0, 0, 0);
+  for (int i = tid; i < hidden / 8; i += 128) reinterpret_cast<uint4*>(ws)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(w) + i);
   float sumv = 0.f;
   if ((ept & 7) == 0) {
     for (int i = 0; i < ept; i += 8) {
@@ -115,15 +122,15 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
   }
   __syncthreads();
   const float rstd = red[0];
-  const int warp = tid >> 5, lane = tid & 31, ng = hidden / 128;
   for (int g = warp; g < ng; g += 4) {
-    const short4 id = *reinterpret_cast<const short4*>(idx + g * 128 + lane * 4);
+    const short4 id = id_next;
+    if (g + 4 < ng) id_next = *reinterpret_cast<const short4*>(idx + (g + 4) * 128 + lane * 4);
     const int ids[4] = {(uint16_t)id.x, (uint16_t)id.y, (uint16_t)id.z, (uint16_t)id.w};
     float v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       // half(float(x) * float(w) * rstd): two FP32 roundings then RN to half (RMSNorm.cuh:150), widened again for the tail
-      const float y = __half2float(xs[ids[i]]) * __half2float(w[ids[i]]) * rstd;
+      const float y = __half2float(xs[ids[i]]) * __half2float(ws[ids[i]]) * rstd;
       v[i] = __half2float(__float2half_rn(y));
     }
     quant_group_store(v, lane, row, g, ng, scale_ldm, s8out, s4out, s8scale, s4scale, hidden);
