@@ -108,10 +108,10 @@ struct GemmOperands {
   int64_t M, N, K;
 };
 
-template <bool kSwap, int BN, int kPack, int kExp, int kSplit, bool kO4>
+template <bool kSwap, int BN, int GS, int kPack, int kSplit, bool kO4, int kConvWarps, int kEpiWgs>
 int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
-  using C = atom::GemmCfg<kSwap, BN, kPack, kExp, kSplit, kO4>;
-  auto kern = atom::gemm_i4_kernel<kSwap, BN, kPack, kExp, kSplit, kO4>;
+  using C = atom::GemmCfg<kSwap, BN, GS, kPack, kSplit, kO4, kConvWarps, kEpiWgs>;
+  auto kern = atom::gemm_i4_kernel<kSwap, BN, GS, kPack, kSplit, kO4, kConvWarps, kEpiWgs>;
   static bool attr_set = false;   // per instantiation; benign race (idempotent)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -149,15 +149,16 @@ int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
 template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
-  if (!skinny) return launch_gemm<false, 128, 4, 3, 1, kO4>(op, args, stream);
+  // <swap, BN, groups per pipeline stage, packed stages, K split, o4, converter warps, epilogue warpgroups>
+  if (!skinny) return launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream);
   // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not
   // cover the machine (the kernel is HBM-bound on the weights: more CTAs = more bytes in flight)
   const int64_t ch_tiles = (op.N + 127) / 128;
   const int groups = args.G + 1;
   const bool split = !(flags & ATOM_GEMM_NO_SPLITK) && groups >= 8 && ch_tiles * ((op.M + 63) / 64) < 120;
-  if (op.M <= 16) return split ? launch_gemm<true, 16, 8, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 16, 8, 3, 1, kO4>(op, args, stream);
-  if (op.M <= 32) return split ? launch_gemm<true, 32, 8, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 32, 8, 3, 1, kO4>(op, args, stream);
-  return split ? launch_gemm<true, 64, 4, 3, 4, kO4>(op, args, stream) : launch_gemm<true, 64, 6, 3, 1, kO4>(op, args, stream);
+  if (op.M <= 16) return split ? launch_gemm<true, 16, 2, 4, 4, kO4, 8, 1>(op, args, stream) : launch_gemm<true, 16, 2, 4, 1, kO4, 8, 1>(op, args, stream);
+  if (op.M <= 32) return split ? launch_gemm<true, 32, 2, 4, 4, kO4, 8, 1>(op, args, stream) : launch_gemm<true, 32, 2, 4, 1, kO4, 8, 1>(op, args, stream);
+  return split ? launch_gemm<true, 64, 1, 4, 4, kO4, 8, 2>(op, args, stream) : launch_gemm<true, 64, 2, 3, 1, kO4, 8, 2>(op, args, stream);
 }
 
 int gemm_common(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,

@@ -7,17 +7,22 @@
 // two scales, FP32 fma accumulation in group order, keeper last, RN cast to half) -- different machine:
 //
 //   TMA (packed INT4 tiles, 64 B rows)  ->  smem "packed ring"
-//   converter warpgroup: nibble -> INT8 (value*16, no sign-extension work) into the canonical
+//   converter warps: nibble -> INT8 (value*16, no sign-extension work) into the canonical
 //       K-major SWIZZLE_128B operand layout ("expanded ring"); the INT8 keeper group is TMA'd straight
 //       into that layout.  Blackwell has no INT4 MMA: kind::i8 is the integer tensor path.
-//   one thread: tcgen05.mma.kind::i8  (128 x BN x 32) x 4 per 128-wide quantisation group, INT32 in TMEM,
-//       a fresh TMEM buffer per group (ring of NB buffers)
+//   one thread: tcgen05.mma.kind::i8  (128 x BN x 32) x 4 per 128-wide quantisation group, INT32 in TMEM
 //   epilogue warpgroups: tcgen05.ld -> acc += float(c) * half(sA*sB) in registers, overlapped with the
-//       MMAs of the following groups; FP16 (o16) or asymmetric INT4 (o4) output.
+//       MMAs of the following stage; FP16 (o16) or asymmetric INT4 (o4) output.
+//
+// A pipeline STAGE is GS quantisation groups, not one: measured on B200 (tools/sync_bench.cu) a warp-to-warp mbarrier
+// hand-off costs ~180 cycles one way, a wait on an already completed phase ~100, a tcgen05.commit ~200 of the issuing
+// thread -- against 256 tensor cycles for one 128x128x128 group.  Every hand-off (TMA->converter->MMA->epilogue) and
+// every commit therefore covers GS groups; one commit per stage serves both the epilogue ("accumulators ready") and
+// the converter ("operand slot free").
 //
 // kSwap=false ("tall"):   MMA-M = 128 tokens (A), MMA-N = BN output channels (B).
 // kSwap=true  ("skinny"): MMA-M = 128 output channels (B), MMA-N = BN tokens (A) -- decode shapes;
-//       optionally split along K over a thread-block cluster, partial sums reduced through DSMEM.
+//       optionally split along K over a thread-block cluster, partial sums pushed into the leader through DSMEM.
 #pragma once
 #include "ptx_sm100.cuh"
 
@@ -38,9 +43,9 @@ struct GemmArgs {
 
 // timeline stamps for pipeline debugging (tools/gpu_check.py trace): slot layout per CTA
 //   0 start | 1 setup done | 2 epilogue loop done | 3 reduction done | 4 end
-//   (first 16 iterations, 8 for the last row) 8+it producer issued | 24+it converter got its expanded slot |
-//   40+it converter saw the packed tile | 56+it conversion stored | 72+it converter fenced+arrived | 88+it MMA thread woke |
-//   104+it accumulator ready (epilogue saw tmem_full) | 120+it epilogue done
+//   per stage s < 16 (8 for the last row): 8+s producer issued | 24+s converter got its operand slot |
+//   40+s converter saw the packed tiles | 56+s conversion stored | 72+s converter fenced+arrived | 88+s MMA thread woke |
+//   104+s accumulators ready (epilogue) | 120+s epilogue done
 __device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
   if (a.trace != nullptr && slot < 128) {
     const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -51,35 +56,37 @@ __device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
 __host__ __device__ __forceinline__ int scale_index(int row) { return (row / 16) * 64 + (row % 8) * 8 + ((row / 8) % 2); }
 __host__ __device__ __forceinline__ int scale_size(int m) { return m / 16 * 64 + 64 - (1 - (m % 16) / 8) * (8 - (m % 8)) * 8; }
 
-template <bool kSwap, int BN, int kPack, int kExp, int kSplit, bool kO4>
+template <bool kSwap, int BN, int GS, int kPack, int kSplit, bool kO4, int kConvWarps, int kEpiWgs>
 struct GemmCfg {
   static constexpr int BM = 128;                                  // MMA M (TMEM lanes)
-  static constexpr int NB = (BN <= 128) ? 4 : 2;                  // TMEM accumulator buffers
-  static constexpr int TMEM_COLS = (NB * BN < 32) ? 32 : NB * BN; // power of two for BN in {16..256}
-  static constexpr int SCALE_SLOTS = 8;                           // scale ring depth (loader runs this far ahead)
-  static constexpr int SCALE_SLOT_BYTES = 512;                    // 256 B MMA-M side + 256 B MMA-N side, raw copies
-  static constexpr int EPI_WGS = (BN >= 64) ? 2 : 1;              // epilogue warpgroups
+  static constexpr int RING = 2;                                  // operand-slot / accumulator stages
+  static constexpr int TMEM_COLS_RAW = RING * GS * BN;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
+  static constexpr int SCALE_STAGES = 4;                          // scale ring depth, in stages
+  static constexpr int SCALE_GROUP_BYTES = 512;                   // 256 B MMA-M side + 256 B MMA-N side, raw copies
+  static constexpr int EPI_WGS = kEpiWgs;                         // epilogue warpgroups (each owns BN/EPI_WGS columns)
   static constexpr int CPT = BN / EPI_WGS;                        // accumulator columns per epilogue thread
-  static constexpr int CONV_WARPS = kSwap ? 8 : 4;                // decode shapes are converter-latency bound: 2 warps / SMSP
+  static constexpr int CONV_WARPS = kConvWarps;
   static constexpr int CONV_THREADS = CONV_WARPS * 32;
   static constexpr int THREADS = 256 + 128 * EPI_WGS + (CONV_WARPS - 4) * 32;   // extra converters sit after the epilogue
-  static constexpr int PACK_P = BM * 64, PACK_Q = BN * 64;        // bytes per packed stage
-  static constexpr int EXP_P = BM * 128, EXP_Q = BN * 128;        // bytes per expanded stage
+  static constexpr int PACK_P = BM * 64, PACK_Q = BN * 64;        // bytes per packed group
+  static constexpr int EXP_P = BM * 128, EXP_Q = (BN * 128 + 1023) / 1024 * 1024;   // bytes per expanded group
   static constexpr int OFF_EXP_P = 0;
-  static constexpr int OFF_EXP_Q = OFF_EXP_P + kExp * EXP_P;
-  static constexpr int OFF_PACK_P = OFF_EXP_Q + kExp * ((EXP_Q + 1023) / 1024 * 1024);
-  static constexpr int OFF_PACK_Q = OFF_PACK_P + kPack * PACK_P;
-  static constexpr int OFF_SM = OFF_PACK_Q + kPack * PACK_Q;      // scale ring (16-B aligned)
+  static constexpr int OFF_EXP_Q = OFF_EXP_P + RING * GS * EXP_P;
+  static constexpr int OFF_PACK_P = OFF_EXP_Q + RING * GS * EXP_Q;
+  static constexpr int OFF_PACK_Q = OFF_PACK_P + kPack * GS * PACK_P;
+  static constexpr int OFF_SM = OFF_PACK_Q + kPack * GS * PACK_Q; // scale ring (16-B aligned)
   static constexpr int RED_BYTES = BM * BN * 4;                   // one rank's split-K partial [col][row] fp32
-  static constexpr int OFF_RED = OFF_SM + SCALE_SLOTS * SCALE_SLOT_BYTES;   // leader only: (kSplit-1) pushed partials
+  static constexpr int OFF_RED = OFF_SM + SCALE_STAGES * GS * SCALE_GROUP_BYTES;   // leader only: pushed partials
   static constexpr int OFF_BAR = OFF_RED + (kSplit > 1 ? (kSplit - 1) * RED_BYTES : 0);
-  static constexpr int NUM_BARS = 2 * kPack + 2 * kExp + 2 * NB + 2 * SCALE_SLOTS;
+  static constexpr int NUM_BARS = 2 * kPack + 3 * RING + 2 * SCALE_STAGES;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;     // + slack for the 1024-B alignment fix-up
   static_assert(!kO4 || (BN == 128 || kSwap), "o4 (tall) quantises one 128-column head per CTA");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(BN <= 128, "scale slot holds 128 channel scales");
-  static_assert(NB * BN <= 512, "TMEM has 512 columns");
+  static_assert(CPT % 16 == 0 && CPT >= 16, "epilogue column slices are multiples of 16");
+  static_assert(TMEM_COLS_RAW <= 512, "TMEM has 512 columns");
 };
 
 // nibble -> int8(value * 16): element 2b of the word lands in byte b of `lo`, element 2b+1 in byte b of `hi`.
@@ -118,33 +125,31 @@ __device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ packed,
   }
 }
 
-template <bool kSwap, int BN, int kPack, int kExp, int kSplit, bool kO4>
-__global__ void __launch_bounds__(GemmCfg<kSwap, BN, kPack, kExp, kSplit, kO4>::THREADS, 1)
+template <bool kSwap, int BN, int GS, int kPack, int kSplit, bool kO4, int kConvWarps, int kEpiWgs>
+__global__ void __launch_bounds__(GemmCfg<kSwap, BN, GS, kPack, kSplit, kO4, kConvWarps, kEpiWgs>::THREADS, 1)
 gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-M operand  (box 64 B x 128 rows)
                const __grid_constant__ CUtensorMap tm_q4,   // packed INT4, MMA-N operand  (box 64 B x BN rows)
                const __grid_constant__ CUtensorMap tm_p8,   // INT8 keeper, MMA-M operand  (box 128 B x 128 rows, SW128)
                const __grid_constant__ CUtensorMap tm_q8,   // INT8 keeper, MMA-N operand  (box 128 B x BN rows, SW128)
                const GemmArgs args) {
-  using C = GemmCfg<kSwap, BN, kPack, kExp, kSplit, kO4>;
+  using C = GemmCfg<kSwap, BN, GS, kPack, kSplit, kO4, kConvWarps, kEpiWgs>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-B alignment (SWIZZLE_128B atoms) by offsetting the shared array, NOT by integer-casting the pointer:
   // an integer round trip makes the compiler fall back to generic LD/ST for every smem access.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* pack_full = bars;
-  uint64_t* pack_empty = pack_full + kPack;
-  uint64_t* exp_full = pack_empty + kPack;
-  uint64_t* exp_empty = exp_full + kExp;
-  uint64_t* tmem_full = exp_empty + kExp;
-  uint64_t* tmem_empty = tmem_full + C::NB;
-  uint64_t* scale_full = tmem_empty + C::NB;
-  uint64_t* scale_empty = scale_full + C::SCALE_SLOTS;
+  uint64_t* pack_full = bars;                          // TMA landed the stage's packed tiles          (1 + tx)
+  uint64_t* pack_empty = pack_full + kPack;            // converters have read them                    (CONV_WARPS)
+  uint64_t* exp_full = pack_empty + kPack;             // expanded operands of the stage are in place  (CONV_WARPS [+ tx])
+  uint64_t* mma_done = exp_full + C::RING;             // the stage's MMAs completed: accumulators ready AND slot reusable (1)
+  uint64_t* tmem_empty = mma_done + C::RING;           // epilogue has read the stage's accumulators   (4 * EPI_WGS)
+  uint64_t* scale_full = tmem_empty + C::RING;         // scales of the stage landed                   (32, cp.async noinc)
+  uint64_t* scale_empty = scale_full + C::SCALE_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile coordinates: blockIdx.x walks the MMA-N operand's tiles fastest? No: x = output-channel tile so that
-  // CTAs launched together share the token tile (L2-resident) and stream disjoint weights.
+  // blockIdx.x = output-channel tile: CTAs launched together share the token tile (L2) and stream disjoint weights
   const int tile_ch = blockIdx.x, tile_tok = blockIdx.y;
   const int p0 = (kSwap ? tile_ch : tile_tok) * C::BM;   // first row of the MMA-M operand
   const int q0 = (kSwap ? tile_tok : tile_ch) * BN;      // first row of the MMA-N operand
@@ -160,28 +165,42 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
     g_begin = min((int)krank * per, total_groups);
     g_end = min(g_begin + per, total_groups);
   }
-  const int iters = g_end - g_begin;
+  const int iters = g_end - g_begin;                        // groups of this CTA
+  const int nstages = (iters + GS - 1) / GS;
+  // stage s covers groups g_begin + s*GS .. ; INT4 groups of a stage travel through the packed ring, the keeper
+  // (only ever the last group of the last stage) goes straight to its operand slot
+  auto stage_groups = [&](int s) { return min(GS, iters - s * GS); };
+  auto stage_int4 = [&](int s) { const int g0 = g_begin + s * GS; return max(0, min(g0 + stage_groups(s), args.G) - g0); };
   if (threadIdx.x == 0) trace_stamp(args, 0);
 
   // ---------------------------------------------------------------- one-time setup
   // Thread 0 initialises the barriers and immediately fires the first kPack stages of TMA loads: the DRAM round trip
   // of the first tiles (the longest latency on the critical path of a decode-sized problem) then overlaps the TMEM
   // allocation and the CTA-wide sync instead of following them.
-  int itp_issued = 0;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_p4); tma_prefetch_desc(&tm_q4); tma_prefetch_desc(&tm_p8); tma_prefetch_desc(&tm_q8);
-    for (int i = 0; i < kPack; ++i) { mbar_init(&pack_full[i], 1); mbar_init(&pack_empty[i], C::CONV_WARPS); }
-    for (int i = 0; i < kExp; ++i) { mbar_init(&exp_full[i], C::CONV_WARPS); mbar_init(&exp_empty[i], 1); }
-    for (int i = 0; i < C::NB; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * C::EPI_WGS); }
-    for (int i = 0; i < C::SCALE_SLOTS; ++i) { mbar_init(&scale_full[i], 32); mbar_init(&scale_empty[i], 4 * C::EPI_WGS); }
-    fence_barrier_init();
-    for (; itp_issued < kPack && itp_issued < iters && g_begin + itp_issued < args.G; ++itp_issued) {
-      const int g = g_begin + itp_issued;
-      mbar_arrive_expect_tx(&pack_full[itp_issued], C::PACK_P + C::PACK_Q);
-      tma_load_2d(smem + C::OFF_PACK_P + itp_issued * C::PACK_P, &tm_p4, &pack_full[itp_issued], g * 64, p0);
-      tma_load_2d(smem + C::OFF_PACK_Q + itp_issued * C::PACK_Q, &tm_q4, &pack_full[itp_issued], g * 64, q0);
-      if (itp_issued < 16) trace_stamp(args, 8 + itp_issued);
+  auto issue_stage = [&](int s, int ps) {
+    const int n4 = stage_int4(s);
+    mbar_arrive_expect_tx(&pack_full[ps], n4 * (C::PACK_P + C::PACK_Q));
+    for (int j = 0; j < n4; ++j) {
+      const int g = g_begin + s * GS + j;
+      tma_load_2d(smem + C::OFF_PACK_P + (ps * GS + j) * C::PACK_P, &tm_p4, &pack_full[ps], g * 64, p0);
+      tma_load_2d(smem + C::OFF_PACK_Q + (ps * GS + j) * C::PACK_Q, &tm_q4, &pack_full[ps], g * 64, q0);
     }
+    if (s < 16) trace_stamp(args, 8 + s);
+  };
+  int s_issued = 0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_p4); tma_prefetch_desc(&tm_q4);
+    // the barriers the first loads need come first; everything else is initialised while those loads are in flight
+    for (int i = 0; i < kPack; ++i) mbar_init(&pack_full[i], 1);
+    fence_barrier_init();
+    for (; s_issued < kPack && s_issued < nstages && stage_int4(s_issued) > 0; ++s_issued) issue_stage(s_issued, s_issued);
+    tma_prefetch_desc(&tm_p8); tma_prefetch_desc(&tm_q8);
+    for (int i = 0; i < kPack; ++i) mbar_init(&pack_empty[i], C::CONV_WARPS);
+    for (int i = 0; i < C::RING; ++i) {
+      mbar_init(&exp_full[i], C::CONV_WARPS); mbar_init(&mma_done[i], 1); mbar_init(&tmem_empty[i], 4 * C::EPI_WGS);
+    }
+    for (int i = 0; i < C::SCALE_STAGES; ++i) { mbar_init(&scale_full[i], 32); mbar_init(&scale_empty[i], 4 * C::EPI_WGS); }
+    fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
   tc_fence_before();
@@ -193,102 +212,100 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
   if (warp == 0) {
     // ============================================================ TMA producer (INT4 groups only)
     if (lane == 0) {
-      int itp = itp_issued;
-      for (int it = itp_issued; it < iters; ++it) {
-        const int g = g_begin + it;
-        if (g >= args.G) break;  // keeper is loaded by the converter straight into the expanded ring
-        const int s = itp % kPack;
-        mbar_wait(&pack_empty[s], ((itp / kPack) & 1) ^ 1);
-        mbar_arrive_expect_tx(&pack_full[s], C::PACK_P + C::PACK_Q);
-        tma_load_2d(smem + C::OFF_PACK_P + s * C::PACK_P, &tm_p4, &pack_full[s], g * 64, p0);
-        tma_load_2d(smem + C::OFF_PACK_Q + s * C::PACK_Q, &tm_q4, &pack_full[s], g * 64, q0);
-        if (it < 16) trace_stamp(args, 8 + it);
-        ++itp;
+      for (int s = s_issued; s < nstages; ++s) {
+        if (stage_int4(s) == 0) break;       // a trailing keeper-only stage has nothing in the packed ring
+        const int ps = s % kPack;
+        mbar_wait(&pack_empty[ps], ((s / kPack) & 1) ^ 1);
+        issue_stage(s, ps);
       }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_i8(C::BM, BN);
-      for (int it = 0; it < iters; ++it) {
-        const int e = it % kExp, b = it % C::NB;
-        mbar_wait(&tmem_empty[b], ((it / C::NB) & 1) ^ 1);
-        mbar_wait(&exp_full[e], (it / kExp) & 1);
+      for (int s = 0; s < nstages; ++s) {
+        const int es = s % C::RING;
+        if (s >= C::RING) mbar_wait(&tmem_empty[es], ((s / C::RING) - 1) & 1);
+        mbar_wait(&exp_full[es], (s / C::RING) & 1);
         tc_fence_after();
-        if (it < 16) trace_stamp(args, 88 + it);
-        const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_P + e * C::EXP_P));
-        const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + e * ((C::EXP_Q + 1023) / 1024 * 1024)));
+        if (s < 16) trace_stamp(args, 88 + s);
+        const int ng = stage_groups(s);
+        for (int j = 0; j < ng; ++j) {
+          const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_P + (es * GS + j) * C::EXP_P));
+          const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + (es * GS + j) * C::EXP_Q));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // 4 x K=32 per 128-wide group; +32 B inside the swizzle atom per step
-          umma_i8(tmem_base + b * BN, dp + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k > 0);
-        umma_commit(&exp_empty[e]);   // smem stage may be refilled once these MMAs have read it
-        umma_commit(&tmem_full[b]);   // accumulator of this group is complete
+          for (int k = 0; k < 4; ++k)   // 4 x K=32 per 128-wide group; +32 B inside the swizzle atom per step
+            umma_i8(tmem_base + (es * GS + j) * BN, dp + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k > 0);
+        }
+        umma_commit(&mma_done[es]);     // one commit per stage: epilogue may read, converter may refill
       }
     }
   } else if (warp == 3) {
     // ============================================================ scale loader: cp.async straight into the scale ring,
     // completion counted on scale_full by the copy engine -- no thread ever waits on a scale's DRAM latency.
-    // Slot layout (raw copies of the reference layouts):
+    // Group slot layout (raw copies of the reference layouts):
     //   [0,256)   MMA-M side: tall  -> 64 (lower,upper) half2 words of the A-scale rows   (word = (r/16)*8 + r%8)
     //                          skinny-> 128 B-scale halves of the channel tile (thread n reads the pair word n/2)
     //   [256,512) MMA-N side: tall  -> BN B-scale halves;  skinny -> BN/16*8 (lower,upper) words of the token rows
-    for (int it = 0; it < iters; ++it) {
-      const int g = g_begin + it;
-      const bool keeper = (g == args.G);
-      const int slot = it % C::SCALE_SLOTS;
-      mbar_wait(&scale_empty[slot], ((it / C::SCALE_SLOTS) & 1) ^ 1);
-      const __half* as_row = keeper ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
-      const __half* bs_row = keeper ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
-      uint8_t* slot_p = smem + C::OFF_SM + slot * C::SCALE_SLOT_BYTES;
-      constexpr int TOK = kSwap ? BN : C::BM, CHN = kSwap ? C::BM : BN;
-      uint8_t* tok_dst = slot_p + (kSwap ? 256 : 0);
-      uint8_t* chn_dst = slot_p + (kSwap ? 0 : 256);
+    for (int s = 0; s < nstages; ++s) {
+      const int ss = s % C::SCALE_STAGES;
+      if (s >= C::SCALE_STAGES) mbar_wait(&scale_empty[ss], ((s / C::SCALE_STAGES) - 1) & 1);
+      const int ng = stage_groups(s);
+      for (int j = 0; j < ng; ++j) {
+        const int g = g_begin + s * GS + j;
+        const bool keeper = (g == args.G);
+        const __half* as_row = keeper ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
+        const __half* bs_row = keeper ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
+        uint8_t* slot_p = smem + C::OFF_SM + (ss * GS + j) * C::SCALE_GROUP_BYTES;
+        constexpr int TOK = kSwap ? BN : C::BM, CHN = kSwap ? C::BM : BN;
+        uint8_t* tok_dst = slot_p + (kSwap ? 256 : 0);
+        uint8_t* chn_dst = slot_p + (kSwap ? 0 : 256);
 #pragma unroll
-      for (int w = lane; w < TOK / 2; w += 32) {              // A-scale words: rows (16 blk + i, 16 blk + i + 8)
-        const int blk = w >> 3, i = w & 7;
-        if (m0 + 16 * blk + i < args.M) cp_async_4(tok_dst + w * 4, as_row + 64 * (m0 / 16 + blk) + 8 * i);
+        for (int w = lane; w < TOK / 2; w += 32) {              // A-scale words: rows (16 blk + i, 16 blk + i + 8)
+          const int blk = w >> 3, i = w & 7;
+          if (m0 + 16 * blk + i < args.M) cp_async_4(tok_dst + w * 4, as_row + 64 * (m0 / 16 + blk) + 8 * i);
+        }
+#pragma unroll
+        for (int c = lane; c < CHN / 8; c += 32)                // B-scale: 8 channels per 16-B chunk
+          if (n0 + 8 * c < args.N) cp_async_16(chn_dst + c * 16, bs_row + n0 + 8 * c);
       }
-#pragma unroll
-      for (int c = lane; c < CHN / 8; c += 32)                // B-scale: 8 channels per 16-B chunk
-        if (n0 + 8 * c < args.N) cp_async_16(chn_dst + c * 16, bs_row + n0 + 8 * c);
-      cp_async_mbar_arrive_noinc(&scale_full[slot]);
+      cp_async_mbar_arrive_noinc(&scale_full[ss]);
     }
   } else if ((warp >= 4 && warp < 8) || warp >= 8 + 4 * C::EPI_WGS) {
-    // ============================================================ converter warps (4, or 8 for decode shapes)
+    // ============================================================ converter warps
     const int t = (warp < 8 ? warp - 4 : warp - 8 - 4 * C::EPI_WGS + 4) * 32 + lane;
-    int itp = 0;
-    for (int it = 0; it < iters; ++it) {
-      const int g = g_begin + it;
-      const bool keeper = (g == args.G);
-      const int e = it % kExp;
-      uint8_t* exp_p = smem + C::OFF_EXP_P + e * C::EXP_P;
-      uint8_t* exp_q = smem + C::OFF_EXP_Q + e * ((C::EXP_Q + 1023) / 1024 * 1024);
-      mbar_wait(&exp_empty[e], ((it / kExp) & 1) ^ 1);
-      if (t == 0 && it < 16) trace_stamp(args, 24 + it);
-      if (!keeper) {
-        const int s = itp % kPack;
-        mbar_wait(&pack_full[s], (itp / kPack) & 1);
-        if (t == 0 && it < 16) trace_stamp(args, 40 + it);
-        convert_tile<C::BM, C::CONV_THREADS>(smem + C::OFF_PACK_P + s * C::PACK_P, exp_p, t);
-        convert_tile<BN, C::CONV_THREADS>(smem + C::OFF_PACK_Q + s * C::PACK_Q, exp_q, t);
-        if (t == 0 && it < 16) trace_stamp(args, 56 + it);
-        fence_proxy_async_smem();     // generic-proxy stores -> visible to tcgen05.mma operand fetch
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&pack_empty[s]); mbar_arrive(&exp_full[e]); }
-        if (t == 0 && it < 16) trace_stamp(args, 72 + it);
-        ++itp;
-      } else {
-        __syncwarp();
-        if (lane == 0) {
-          if (t == 0) {
-            mbar_arrive_expect_tx(&exp_full[e], C::EXP_P + C::EXP_Q);
-            tma_load_2d(exp_p, &tm_p8, &exp_full[e], 0, p0);
-            tma_load_2d(exp_q, &tm_q8, &exp_full[e], 0, q0);
-          } else {
-            mbar_arrive(&exp_full[e]);
+    for (int s = 0; s < nstages; ++s) {
+      const int es = s % C::RING, ps = s % kPack;
+      const int ng = stage_groups(s), n4 = stage_int4(s);
+      if (s >= C::RING) mbar_wait(&mma_done[es], ((s / C::RING) - 1) & 1);   // MMAs that read this slot have completed
+      if (t == 0 && s < 16) trace_stamp(args, 24 + s);
+      if (n4 > 0) {
+        mbar_wait(&pack_full[ps], (s / kPack) & 1);
+        if (t == 0 && s < 16) trace_stamp(args, 40 + s);
+#pragma unroll
+        for (int j = 0; j < GS; ++j) {
+          if (j < n4) {
+            convert_tile<C::BM, C::CONV_THREADS>(smem + C::OFF_PACK_P + (ps * GS + j) * C::PACK_P,
+                                                 smem + C::OFF_EXP_P + (es * GS + j) * C::EXP_P, t);
+            convert_tile<BN, C::CONV_THREADS>(smem + C::OFF_PACK_Q + (ps * GS + j) * C::PACK_Q,
+                                              smem + C::OFF_EXP_Q + (es * GS + j) * C::EXP_Q, t);
           }
         }
+        if (t == 0 && s < 16) trace_stamp(args, 56 + s);
+        fence_proxy_async_smem();     // generic-proxy stores -> visible to tcgen05.mma operand fetch
       }
+      __syncwarp();
+      if (lane == 0) {
+        if (n4 > 0) mbar_arrive(&pack_empty[ps]);
+        if (n4 < ng && t == 0) {        // the keeper is this stage's last group: TMA it into its operand slot
+          mbar_arrive_expect_tx(&exp_full[es], C::EXP_P + BN * 128);
+          tma_load_2d(smem + C::OFF_EXP_P + (es * GS + n4) * C::EXP_P, &tm_p8, &exp_full[es], 0, p0);
+          tma_load_2d(smem + C::OFF_EXP_Q + (es * GS + n4) * C::EXP_Q, &tm_q8, &exp_full[es], 0, q0);
+        } else {
+          mbar_arrive(&exp_full[es]);
+        }
+      }
+      if (t == 0 && s < 16) trace_stamp(args, 72 + s);
     }
   } else if (warp >= 8 && warp < 8 + 4 * C::EPI_WGS) {
     // ============================================================ epilogue warpgroup(s)
@@ -301,77 +318,79 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
     const bool upper = kSwap ? false : (((m0 + row) & 15) >= 8);
     const uint32_t pair_sel = upper ? 0x7632u : 0x5410u;   // one PRMT picks the odd (upper rows) or even channel of two pairs
 
-    for (int it = 0; it < iters; ++it) {
-      const int g = g_begin + it;
-      const bool keeper = (g == args.G);
-      const int slot = it % C::SCALE_SLOTS, b = it % C::NB;
-      mbar_wait(&scale_full[slot], (it / C::SCALE_SLOTS) & 1);
-      const uint8_t* slot_p = smem + C::OFF_SM + slot * C::SCALE_SLOT_BYTES;
-      __half2 sm2;
-      const __half* sn;      // tall: B-scale halves of this thread's columns
-      const __half2* snw;    // skinny: (lower, upper) A-scale words of this thread's token columns
-      if constexpr (!kSwap) {
-        const __half2 pw = reinterpret_cast<const __half2*>(slot_p)[(row >> 4) * 8 + (row & 7)];
-        sm2 = __half2half2(upper ? __high2half(pw) : __low2half(pw));
-        sn = reinterpret_cast<const __half*>(slot_p + 256) + colbase;
-        snw = nullptr;
-      } else {
-        sm2 = reinterpret_cast<const __half2*>(slot_p)[row >> 1];     // {sB[n&~1], sB[n|1]}
-        sn = nullptr;
-        snw = reinterpret_cast<const __half2*>(slot_p + 256) + (colbase >> 4) * 8;
-      }
-      mbar_wait(&tmem_full[b], (it / C::NB) & 1);
+    for (int s = 0; s < nstages; ++s) {
+      const int es = s % C::RING, ss = s % C::SCALE_STAGES;
+      const int ng = stage_groups(s);
+      mbar_wait(&scale_full[ss], (s / C::SCALE_STAGES) & 1);
+      mbar_wait(&mma_done[es], (s / C::RING) & 1);
       tc_fence_after();
-      if (warp == 8 && lane == 0 && it < 16) trace_stamp(args, 104 + it);
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * BN + colbase);
-      constexpr int CH = (C::CPT >= 32) ? 32 : 16;
-#pragma unroll
-      for (int c0 = 0; c0 < C::CPT; c0 += CH) {
-        uint32_t r[CH];
-        if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r); else tmem_ld_32x32b_x16(taddr + c0, r);
-        tmem_ld_wait();
-        if (c0 + CH == C::CPT) {      // whole accumulator buffer is in registers: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[b]);
-        }
-        // INT4 groups carry a factor 256 (both operands are value*16); lift the keeper to the same domain
-        if (keeper) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) r[j] = (uint32_t)((int32_t)r[j] << 8);
-        }
+      if (warp == 8 && lane == 0 && s < 16) trace_stamp(args, 104 + s);
+      for (int j = 0; j < ng; ++j) {
+        const bool keeper = (g_begin + s * GS + j == args.G);
+        const uint8_t* slot_p = smem + C::OFF_SM + (ss * GS + j) * C::SCALE_GROUP_BYTES;
+        __half2 sm2;
+        const __half* sn;      // tall: B-scale halves of this thread's columns
+        const __half2* snw;    // skinny: (lower, upper) A-scale words of this thread's token columns
         if constexpr (!kSwap) {
-          // thread = token row; columns = channels.  rs is shared by the column pair (2p, 2p+1).
-#pragma unroll
-          for (int p = 0; p < CH / 2; p += 2) {
-            const __half2 n01 = *reinterpret_cast<const __half2*>(sn + c0 + 2 * p);
-            const __half2 n23 = *reinterpret_cast<const __half2*>(sn + c0 + 2 * p + 2);
-            const uint32_t selw = __byte_perm(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23), pair_sel);
-            const __half2 sel = *reinterpret_cast<const __half2*>(&selw);   // {sB[pair p], sB[pair p+1]} for this row's half
-            const float2 rs = __half22float2(__hmul2(sm2, sel));
-            acc[c0 + 2 * p + 0] = fmaf((float)(int32_t)r[2 * p + 0], rs.x, acc[c0 + 2 * p + 0]);
-            acc[c0 + 2 * p + 1] = fmaf((float)(int32_t)r[2 * p + 1], rs.x, acc[c0 + 2 * p + 1]);
-            acc[c0 + 2 * p + 2] = fmaf((float)(int32_t)r[2 * p + 2], rs.y, acc[c0 + 2 * p + 2]);
-            acc[c0 + 2 * p + 3] = fmaf((float)(int32_t)r[2 * p + 3], rs.y, acc[c0 + 2 * p + 3]);
-          }
+          const __half2 pw = reinterpret_cast<const __half2*>(slot_p)[(row >> 4) * 8 + (row & 7)];
+          sm2 = __half2half2(upper ? __high2half(pw) : __low2half(pw));
+          sn = reinterpret_cast<const __half*>(slot_p + 256) + colbase;
+          snw = nullptr;
         } else {
-          // thread = channel row (sm2 = {sB[n&~1], sB[n|1]}); columns = tokens, 16-aligned tile origin:
-          // token j with j%16<8 pairs with sm2.x, j%16>=8 with sm2.y
+          sm2 = reinterpret_cast<const __half2*>(slot_p)[row >> 1];     // {sB[n&~1], sB[n|1]}
+          sn = nullptr;
+          snw = reinterpret_cast<const __half2*>(slot_p + 256) + (colbase >> 4) * 8;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((es * GS + j) * BN + colbase);
+        constexpr int CH = (C::CPT >= 32) ? 32 : 16;
 #pragma unroll
-          for (int j = 0; j < CH; j += 16) {
+        for (int c0 = 0; c0 < C::CPT; c0 += CH) {
+          uint32_t r[CH];
+          if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r); else tmem_ld_32x32b_x16(taddr + c0, r);
+          tmem_ld_wait();
+          if (c0 + CH == C::CPT && j == ng - 1) {   // the stage's accumulators are in registers: hand TMEM back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[es]);
+          }
+          // INT4 groups carry a factor 256 (both operands are value*16); lift the keeper to the same domain
+          if (keeper) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const __half2 a2 = snw[((c0 + j) >> 4) * 8 + i];      // (sA[token j+i], sA[token j+i+8])
-              const float2 rs = __half22float2(__hmul2(a2, sm2));
-              acc[c0 + j + i] = fmaf((float)(int32_t)r[j + i], rs.x, acc[c0 + j + i]);
-              acc[c0 + j + i + 8] = fmaf((float)(int32_t)r[j + i + 8], rs.y, acc[c0 + j + i + 8]);
+            for (int i = 0; i < CH; ++i) r[i] = (uint32_t)((int32_t)r[i] << 8);
+          }
+          if constexpr (!kSwap) {
+            // thread = token row; columns = channels.  rs is shared by the column pair (2p, 2p+1).
+#pragma unroll
+            for (int p = 0; p < CH / 2; p += 2) {
+              const __half2 n01 = *reinterpret_cast<const __half2*>(sn + c0 + 2 * p);
+              const __half2 n23 = *reinterpret_cast<const __half2*>(sn + c0 + 2 * p + 2);
+              const uint32_t selw = __byte_perm(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23), pair_sel);
+              const __half2 sel = *reinterpret_cast<const __half2*>(&selw);   // {sB[pair p], sB[pair p+1]} for this row's half
+              const float2 rs = __half22float2(__hmul2(sm2, sel));
+              acc[c0 + 2 * p + 0] = fmaf((float)(int32_t)r[2 * p + 0], rs.x, acc[c0 + 2 * p + 0]);
+              acc[c0 + 2 * p + 1] = fmaf((float)(int32_t)r[2 * p + 1], rs.x, acc[c0 + 2 * p + 1]);
+              acc[c0 + 2 * p + 2] = fmaf((float)(int32_t)r[2 * p + 2], rs.y, acc[c0 + 2 * p + 2]);
+              acc[c0 + 2 * p + 3] = fmaf((float)(int32_t)r[2 * p + 3], rs.y, acc[c0 + 2 * p + 3]);
+            }
+          } else {
+            // thread = channel row (sm2 = {sB[n&~1], sB[n|1]}); columns = tokens, 16-aligned tile origin:
+            // token i with i%16<8 pairs with sm2.x, i%16>=8 with sm2.y
+#pragma unroll
+            for (int q = 0; q < CH; q += 16) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const __half2 a2 = snw[((c0 + q) >> 4) * 8 + i];      // (sA[token q+i], sA[token q+i+8])
+                const float2 rs = __half22float2(__hmul2(a2, sm2));
+                acc[c0 + q + i] = fmaf((float)(int32_t)r[q + i], rs.x, acc[c0 + q + i]);
+                acc[c0 + q + i + 8] = fmaf((float)(int32_t)r[q + i + 8], rs.y, acc[c0 + q + i + 8]);
+              }
             }
           }
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&scale_empty[slot]);       // this warp no longer reads the slot
-      if (warp == 8 && lane == 0 && it < 8) trace_stamp(args, 120 + it);
+      if (lane == 0) mbar_arrive(&scale_empty[ss]);       // this warp no longer reads the stage's scales
+      if (warp == 8 && lane == 0 && s < 8) trace_stamp(args, 120 + s);
     }
     if (warp == 8 && lane == 0) trace_stamp(args, 2);
 
@@ -435,27 +454,34 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
           float mx = -INFINITY, mn = INFINITY;
 #pragma unroll
           for (int i = 0; i < C::CPT; ++i) { acc[i] *= kInv; const float a = fabsf(acc[i]); mx = fmaxf(mx, a); mn = fminf(mn, a); }
-          const int half_id = (warp - 8) >> 2;
-          xch[(half_id * 2 + 0) * C::BM + row] = mx;
-          xch[(half_id * 2 + 1) * C::BM + row] = mn;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          mx = fmaxf(mx, xch[((half_id ^ 1) * 2 + 0) * C::BM + row]);
-          mn = fminf(mn, xch[((half_id ^ 1) * 2 + 1) * C::BM + row]);
+          const int part = (warp - 8) >> 2;          // which column slice of the 128-channel head this warpgroup holds
+          xch[(part * 2 + 0) * C::BM + row] = mx;
+          xch[(part * 2 + 1) * C::BM + row] = mn;
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * C::EPI_WGS) : "memory");
+#pragma unroll
+          for (int o = 0; o < C::EPI_WGS; ++o) {
+            mx = fmaxf(mx, xch[(o * 2 + 0) * C::BM + row]);
+            mn = fminf(mn, xch[(o * 2 + 1) * C::BM + row]);
+          }
           const float scale = (mx - mn) / 15.f, zero = -mn, r_scale = 1.f / scale;
           const int m = m0 + row;
           if (m < args.M) {
-            if (half_id == 0) args.d_scale[(size_t)m * (args.N / 128) + tile_ch] = __floats2half2_rn(scale, zero);
+            if (part == 0) args.d_scale[(size_t)m * (args.N / 128) + tile_ch] = __floats2half2_rn(scale, zero);
             uint32_t pk[C::CPT / 8];
 #pragma unroll
             for (int i = 0; i < C::CPT; i += 8) {
               uint32_t w = 0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) w |= ((uint32_t)((int)roundf((acc[i + j] + zero) * r_scale) & 0xF)) << (4 * j);
+              for (int e = 0; e < 8; ++e) w |= ((uint32_t)((int)roundf((acc[i + e] + zero) * r_scale) & 0xF)) << (4 * e);
               pk[i / 8] = w;
             }
             uint4* dst = reinterpret_cast<uint4*>(args.d4 + (size_t)m * (args.N / 2) + (n0 + colbase) / 2);
+            if constexpr (C::CPT >= 32) {
 #pragma unroll
-            for (int i = 0; i < C::CPT / 32; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+              for (int i = 0; i < C::CPT / 32; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            } else {
+              *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[1]);
+            }
           }
         } else {
           // skinny: thread = channel; reduce |v| min/max over the 128 channels of the head for every token column
@@ -471,8 +497,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
             for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
             if (lane == 0) { xmx[(ewarp & 3) * BN + colbase + i] = mx; xmn[(ewarp & 3) * BN + colbase + i] = mn; }
           }
-          if constexpr (C::EPI_WGS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
-          else asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * C::EPI_WGS) : "memory");
           const int n = n0 + row;
 #pragma unroll
           for (int i = 0; i < C::CPT; ++i) {
