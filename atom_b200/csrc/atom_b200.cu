@@ -206,7 +206,7 @@ int atom_reorder_fp16_i4(const void* hidden, const void* reorder_index, int seq_
   ATOM_REQUIRE(hidden && reorder_index && aligned16(hidden), "reorder_fp16_i4: null or misaligned input");
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(atom::reorder_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072); attr_set = true; }
-  atom::reorder_quant_kernel<<<seq_len, 256, (size_t)hidden_dim * 2, (cudaStream_t)stream>>>(
+  atom::reorder_quant_kernel<<<seq_len, atom::QUANT_THREADS, (size_t)hidden_dim * 2, (cudaStream_t)stream>>>(
       (const __half*)hidden, (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms,
       (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
   return check_launch("reorder_fp16_i4");
@@ -221,7 +221,7 @@ int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, cons
   ATOM_REQUIRE(hidden_dim <= 32768, "rmsnorm_fp16_i4: hidden_dim=%d > 32768 unsupported", hidden_dim);
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(atom::rmsnorm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 * 2 / 2 + 65536 + 512); attr_set = true; }
-  atom::rmsnorm_quant_kernel<<<seq_len, 128, (size_t)hidden_dim * 4 + 512, (cudaStream_t)stream>>>(
+  atom::rmsnorm_quant_kernel<<<seq_len, atom::QUANT_THREADS, (size_t)hidden_dim * 4 + 512, (cudaStream_t)stream>>>(
       (const __half*)hidden, (const __half*)weight, eps, (const int16_t*)reorder_index, seq_len, hidden_dim,
       (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
   return check_launch("rmsnorm_fp16_i4");

@@ -48,8 +48,9 @@ __device__ __forceinline__ void quant_group_store(const float (&v)[4], int lane,
 }
 
 // ---------------------------------------------------------------- K3: reorder + quantise
-// grid = rows, block = 256 (8 warps); the row is staged in smem once, every warp gathers its groups from there.
-__global__ void __launch_bounds__(256)
+// grid = rows, block = 512 (16 warps); the row is staged in smem once, every warp gathers its groups from there.
+constexpr int QUANT_THREADS = 512, QUANT_WARPS = QUANT_THREADS / 32;
+__global__ void __launch_bounds__(QUANT_THREADS)
 reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ idx, int seq_len, int hidden,
                      int8_t* __restrict__ s8out, uint8_t* __restrict__ s4out, __half* __restrict__ s8scale,
                      __half* __restrict__ s4scale, int scale_ldm) {
@@ -61,9 +62,9 @@ reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ i
   const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * hidden);
   for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) reinterpret_cast<uint4*>(xs)[i] = ld_nc_v4(src + i);
   __syncthreads();
-  for (int g = warp; g < ng; g += 8) {
+  for (int g = warp; g < ng; g += QUANT_WARPS) {
     const short4 id = id_next;
-    if (g + 8 < ng) id_next = *reinterpret_cast<const short4*>(idx + (g + 8) * 128 + lane * 4);
+    if (g + QUANT_WARPS < ng) id_next = *reinterpret_cast<const short4*>(idx + (g + QUANT_WARPS) * 128 + lane * 4);
     float v[4] = {__half2float(xs[(uint16_t)id.x]), __half2float(xs[(uint16_t)id.y]), __half2float(xs[(uint16_t)id.z]),
                   __half2float(xs[(uint16_t)id.w])};
     quant_group_store(v, lane, row, g, ng, scale_ldm, s8out, s4out, s8scale, s4scale, hidden);
@@ -71,10 +72,12 @@ reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ i
 }
 
 // ---------------------------------------------------------------- K4: RMSNorm + reorder + quantise
-// grid = rows, block = 128.  The sum of squares keeps the reference's association so that rstd -- and with it
-// every quantised value -- is bit-identical: thread t folds hidden/128 contiguous elements with fmaf, then
-// s[t]+=s[t+64], s[t]+=s[t+32], then shfl_down 16..1 (RMSNorm.cuh:112-141).
-__global__ void __launch_bounds__(128)
+// grid = rows, block = 512.  The sum of squares keeps the reference's association so that rstd -- and with it
+// every quantised value -- is bit-identical: thread t < 128 folds hidden/128 contiguous elements with fmaf, then
+// s[t]+=s[t+64], s[t]+=s[t+32], then shfl_down 16..1 (RMSNorm.cuh:112-141).  The other 12 warps meanwhile stage
+// the norm weight; afterwards all 16 warps quantise groups (at decode sizes the kernel is one latency chain per row,
+// so the chain is kept short: 2 groups per warp at hidden 4096 instead of 8).
+__global__ void __launch_bounds__(QUANT_THREADS)
 rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w, float eps, const int16_t* __restrict__ idx,
                      int seq_len, int hidden, int8_t* __restrict__ s8out, uint8_t* __restrict__ s4out,
                      __half* __restrict__ s8scale, __half* __restrict__ s4scale, int scale_ldm) {
@@ -88,9 +91,11 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
   const __half* xr = x + (size_t)row * hidden;
   // independent loads first: the first group's reorder indices and the weight row travel while the row is reduced
   short4 id_next = (warp < ng) ? *reinterpret_cast<const short4*>(idx + warp * 128 + lane * 4) : make_short4(0, 0, 0, 0);
-  for (int i = tid; i < hidden / 8; i += 128) reinterpret_cast<uint4*>(ws)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(w) + i);
   float sumv = 0.f;
-  if ((ept & 7) == 0) {
+  if (tid >= 128) {
+    for (int i = tid - 128; i < hidden / 8; i += QUANT_THREADS - 128)
+      reinterpret_cast<uint4*>(ws)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(w) + i);
+  } else if ((ept & 7) == 0) {
     for (int i = 0; i < ept; i += 8) {
       const uint4 u = *reinterpret_cast<const uint4*>(xr + tid * ept + i);
       *reinterpret_cast<uint4*>(xs + tid * ept + i) = u;
@@ -110,7 +115,7 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
       sumv = fmaf(f, f, sumv);
     }
   }
-  red[tid] = sumv;
+  if (tid < 128) red[tid] = sumv;
   __syncthreads();
   if (tid < 64) red[tid] = sumv = sumv + red[tid + 64];
   __syncthreads();
@@ -122,9 +127,9 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
   }
   __syncthreads();
   const float rstd = red[0];
-  for (int g = warp; g < ng; g += 4) {
+  for (int g = warp; g < ng; g += QUANT_WARPS) {
     const short4 id = id_next;
-    if (g + 4 < ng) id_next = *reinterpret_cast<const short4*>(idx + (g + 4) * 128 + lane * 4);
+    if (g + QUANT_WARPS < ng) id_next = *reinterpret_cast<const short4*>(idx + (g + QUANT_WARPS) * 128 + lane * 4);
     const int ids[4] = {(uint16_t)id.x, (uint16_t)id.y, (uint16_t)id.z, (uint16_t)id.w};
     float v[4];
 #pragma unroll
