@@ -155,10 +155,23 @@ int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t f
   // cover the machine (the kernel is HBM-bound on the weights: more CTAs = more bytes in flight)
   const int64_t ch_tiles = (op.N + 127) / 128;
   const int groups = args.G + 1;
-  const bool split = !(flags & ATOM_GEMM_NO_SPLITK) && groups >= 8 && ch_tiles * ((op.M + 63) / 64) < 120;
-  if (op.M <= 16) return split ? launch_gemm<true, 16, 2, 4, 4, kO4, 8, 1>(op, args, stream) : launch_gemm<true, 16, 2, 4, 1, kO4, 8, 1>(op, args, stream);
-  if (op.M <= 32) return split ? launch_gemm<true, 32, 2, 4, 4, kO4, 8, 1>(op, args, stream) : launch_gemm<true, 32, 2, 4, 1, kO4, 8, 1>(op, args, stream);
-  return split ? launch_gemm<true, 64, 1, 4, 4, kO4, 8, 2>(op, args, stream) : launch_gemm<true, 64, 2, 3, 1, kO4, 8, 2>(op, args, stream);
+  // K split over a cluster (1, 2 or 4 ranks): as many CTAs as it takes to give every SM about one, no more -- each extra
+  // wave of CTAs costs a full pipeline ramp (first TMA tile ~2 us after launch).
+  const int64_t tiles = ch_tiles * ((op.M + 63) / 64);
+  int ksplit = 1;
+  if (!(flags & ATOM_GEMM_NO_SPLITK) && groups >= 8) {
+    if (flags & ATOM_GEMM_SPLITK2) ksplit = 2;
+    else if (flags & ATOM_GEMM_SPLITK4) ksplit = 4;
+    else ksplit = tiles * 4 <= 148 ? 4 : (tiles * 2 <= 148 ? 2 : 1);   // the largest split that still fits one wave of 148 SMs
+  }
+#define ATOM_SKINNY(BN, GS4, GS2, GS1, KP4, KP2, KP1, EW)                                                      \
+  return ksplit == 4   ? launch_gemm<true, BN, GS4, KP4, 4, kO4, 8, EW>(op, args, stream)                      \
+         : ksplit == 2 ? launch_gemm<true, BN, GS2, KP2, 2, kO4, 8, EW>(op, args, stream)                      \
+                       : launch_gemm<true, BN, GS1, KP1, 1, kO4, 8, EW>(op, args, stream)
+  if (op.M <= 16) { ATOM_SKINNY(16, 2, 2, 2, 4, 4, 4, 1); }
+  if (op.M <= 32) { ATOM_SKINNY(32, 2, 2, 2, 4, 4, 4, 1); }
+  ATOM_SKINNY(64, 1, 2, 2, 4, 2, 3, 2);
+#undef ATOM_SKINNY
 }
 
 int gemm_common(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,

@@ -40,6 +40,8 @@ extern "C" {
 #define ATOM_GEMM_NO_SPLITK 1u   /* bit-exact accumulation order (groups 0..G-1 then keeper) even for small M */
 #define ATOM_GEMM_FORCE_TALL 2u  /* tokens on the MMA-M axis regardless of M */
 #define ATOM_GEMM_FORCE_SKINNY 4u /* channels on the MMA-M axis (requires M <= 128 per tile; any M works) */
+#define ATOM_GEMM_SPLITK2 16u     /* decode shapes: force a 2-way K split (default: chosen from the tile count) */
+#define ATOM_GEMM_SPLITK4 32u     /* decode shapes: force a 4-way K split */
 
 ATOM_API int atom_version(void);
 ATOM_API const char* atom_last_error(void);
