@@ -285,12 +285,18 @@ int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, const void
   ATOM_REQUIRE(aligned16(kv_data) && aligned16(kv_param), "batch_decode_i4: KV pool must be 16-byte aligned");
   atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
                   (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
-  const size_t smem = (size_t)atom::DEC_STAGES * (136 * page_size) + (size_t)page_size * 64 * 8 + 64 * 8 + 4 * 4 * 34 * 4 +
-                      2 * atom::DEC_STAGES * 8 + 128;
+  const size_t smem = (size_t)atom::DEC_STAGES * (136 * page_size) + (size_t)8 * page_size * 4 * 8 + 64 * 8 + 4 * 64 * 8 +
+                      4 * 4 * 34 * 4 + 2 * atom::DEC_STAGES * 8 + 128;
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(atom::batch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 136 * 64 + 64 * 64 * 8 + 8192); attr_set = true; }
-  atom::batch_decode_kernel<<<dim3(batch_size, num_heads), atom::DEC_THREADS, smem, (cudaStream_t)stream>>>(
-      (__half*)o, (const __half*)q, kv);
+  if (!attr_set) {
+    cudaFuncSetAttribute(atom::batch_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(atom::batch_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  if (page_size <= 32)
+    atom::batch_decode_kernel<4><<<dim3(batch_size, num_heads), atom::DEC_THREADS, smem, (cudaStream_t)stream>>>((__half*)o, (const __half*)q, kv);
+  else
+    atom::batch_decode_kernel<8><<<dim3(batch_size, num_heads), atom::DEC_THREADS, smem, (cudaStream_t)stream>>>((__half*)o, (const __half*)q, kv);
   return check_launch("batch_decode_i4");
 }
 

@@ -57,37 +57,45 @@ append_kv_kernel(KvArgs kv, const uint8_t* __restrict__ k, const uint8_t* __rest
 
 // ---------------------------------------------------------------- K6: batch decode
 // grid (B, H), 160 threads: warp 4 streams whole pages (K block, V block and their params are each contiguous) into an
-// 8-stage smem ring with cp.async.bulk + mbarrier complete_tx -- enough bytes in flight per SM to cover HBM latency
-// (a register-load version of this kernel was latency bound at 0.8 TB/s).  Warp w < 4 consumes pages w, w+4, ...
-// Inside a page a lane = (token slot ts = lane/4, quarter c = lane%4) handles tokens ts, ts+8, ...: for QK it holds the
-// RoPE pairs i = 16c..16c+15 (elements i and i+64), for PV the V elements 32c..32c+31.
+// 8-stage smem ring with cp.async.bulk + mbarrier complete_tx -- enough bytes in flight per SM to cover HBM latency.
+// Warp w < 4 consumes pages w, w+4, ...  Inside a page a lane = (token slot ts = lane/4, quarter c = lane%4) handles
+// tokens ts, ts+8, ...: for QK it holds the RoPE pairs i = 16c..16c+15 (elements i and i+64), for PV the V elements
+// 32c..32c+31.
 // RoPE: with z = x_i + j x_{i+64}, rope(x, p) = z e^{j p theta_i} and q.k = Re(zq conj(zk)), so
 //   score(t) = Re( [zq e^{j(len-1)theta} e^{-j pagebase theta}] * conj( zk e^{j t_lo theta} ) ):
-// the bracket is advanced once per page by a constant rotation, e^{j t_lo theta} comes from a P x 64 smem table -- no
-// transcendental per token (the reference evaluates __sincosf per element per token, decode.cuh:39-71).
-// Softmax is blocked per page: one rescale of the accumulator per page instead of per token.
-// V dequant is folded: sum_t p_t (n s_t - z_t) = sum_t (p_t s_t) n - sum_t p_t z_t (the last sum is a scalar).
+// the bracket is advanced once per page by a constant rotation (FP32, kept in smem), e^{j t_lo theta} comes from a smem
+// table -- no transcendental per token (the reference evaluates __sincosf per element per token, decode.cuh:39-71).
+// The per-token arithmetic runs in packed half2: one LOP3 turns two nibbles into the halves (1024+n); HSUB2 makes them
+// exact; dequant, rotation and the q.k products are HFMA2 on nibble couples (j, j+4); scores, softmax statistics, the
+// page-level rescale and the output accumulators stay FP32 (V is accumulated in half2 only within one page).  An
+// all-FP32 version of this kernel executed 75 M warp instructions per layer, 36 % of them nibble extraction/conversion.
+// Softmax is blocked per page; V dequant is folded: sum_t p_t (n s_t - z_t) = sum_t (p_t s_t) n - sum_t p_t z_t.
 constexpr int DEC_CONSUMERS = 4;
 constexpr int DEC_THREADS = 32 * (DEC_CONSUMERS + 1);
 constexpr int DEC_STAGES = 8;
-constexpr int DEC_MAX_TPL = 8;   // tokens per lane per page = P / 8  (P <= 64)
-
-__device__ __forceinline__ float nib_f(uint32_t w, int e) { return (float)((w >> (4 * e)) & 0xFu); }
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// nibbles q and q+4 of `w` as exact halves: ((w >> 4q) & 0x000F000F) | 0x64006400 = (1024+n_q, 1024+n_{q+4}), minus 1024
+__device__ __forceinline__ __half2 nib2(uint32_t w, int q) {
+  const uint32_t u = ((w >> (4 * q)) & 0x000F000Fu) | 0x64006400u;
+  return __hsub2(*reinterpret_cast<const __half2*>(&u), __half2half2(__ushort_as_half(0x6400)));
+}
+
+template <int kMaxTpl>   // tokens per lane per page = P / 8 <= kMaxTpl
 __global__ void __launch_bounds__(DEC_THREADS, 4)
 batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs kv) {
   extern __shared__ __align__(128) uint8_t smem_d[];
   const int P = kv.P;
   const int stage_bytes = 2 * 64 * P + 2 * 4 * P;                   // K | V | K params | V params
   uint8_t* ring = smem_d;
-  float2* tab = reinterpret_cast<float2*>(smem_d + DEC_STAGES * stage_bytes);   // [P][64]  (cos, sin)(t_lo * theta_i)
-  float2* stepr = tab + P * 64;                                     // [64]     e^{-j 4P theta_i}
-  float* merge = reinterpret_cast<float*>(stepr + 64);              // [4 warps][4 quarters][34]
+  uint2* tabh = reinterpret_cast<uint2*>(smem_d + DEC_STAGES * stage_bytes);    // [8 couples][P][4 quarters] (cos2, sin2) half2
+  float2* stepr = reinterpret_cast<float2*>(tabh + 8 * P * 4);     // [64]     e^{-j 4P theta_i}
+  float2* brk = stepr + 64;                                         // [4 warps][64] FP32 query bracket per warp
+  float* merge = reinterpret_cast<float*>(brk + 4 * 64);            // [4 warps][4 quarters][34]
   uint64_t* full = reinterpret_cast<uint64_t*>(merge + 4 * 4 * 34);
   uint64_t* empty = full + DEC_STAGES;
 
@@ -103,19 +111,33 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
     for (int i = 0; i < DEC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     fence_barrier_init();
   }
-  // table layout [j/2][t_lo][c][j%2] (pair = 16c + j): for a fixed j the 32 lanes (t_lo = ts + 8i, c) of a warp read 32
-  // consecutive 16-B words -- conflict free.  (A [t_lo][pair] layout put all 32 lanes on the same bank: 82 % of the
-  // kernel's shared-memory wavefronts were conflict replays.)
-  for (int i = tid; i < P * 64; i += DEC_THREADS) {
-    const int tl = i >> 6, pair = i & 63, cc = pair >> 4, j = pair & 15;
-    const float f = exp2f(-(float)pair * (kLog2Theta / 64.f));
-    float sn, cs; sincosf((float)tl * f, &sn, &cs);
-    tab[(((j >> 1) * P + tl) * 4 + cc) * 2 + (j & 1)] = make_float2(cs, sn);
+  // table entry (u, tl, c): couple u = (j_a, j_a+4) with j_a = 8(u/4) + u%4, pair index i = 16c + j.  For a fixed u the
+  // 32 lanes (tl = ts + 8k, c) of a warp read 32 consecutive 8-B words: conflict free.
+  for (int e = tid; e < 8 * P * 4; e += DEC_THREADS) {
+    const int cc = e & 3, tl = (e >> 2) % P, u = e / (4 * P);
+    const int ja = 8 * (u >> 2) + (u & 3);
+    float sa, ca, sb, cb;
+    sincosf((float)tl * exp2f(-(float)(16 * cc + ja) * (kLog2Theta / 64.f)), &sa, &ca);
+    sincosf((float)tl * exp2f(-(float)(16 * cc + ja + 4) * (kLog2Theta / 64.f)), &sb, &cb);
+    const __half2 c2 = __floats2half2_rn(ca, cb), s2 = __floats2half2_rn(sa, sb);
+    tabh[e] = make_uint2(*reinterpret_cast<const uint32_t*>(&c2), *reinterpret_cast<const uint32_t*>(&s2));
   }
   if (tid < 64) {
     const float f = exp2f(-(float)tid * (kLog2Theta / 64.f));
     float sn, cs; sincosf((float)(DEC_CONSUMERS * P) * f, &sn, &cs);
     stepr[tid] = make_float2(cs, -sn);
+  }
+  if (warp < DEC_CONSUMERS && ts == 0) {
+    // FP32 query bracket of this warp: zq e^{j (len-1 - warp*P) theta}; 4 lanes (c) x 16 pairs
+    const __half* qh = q + ((size_t)b * kv.H + h) * 128;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = 16 * c + j;
+      const float f = exp2f(-(float)i * (kLog2Theta / 64.f));
+      const float xr = __half2float(qh[i]), xi = __half2float(qh[i + 64]);
+      float sn, cs; sincosf((float)(seq_len - 1 - warp * P) * f, &sn, &cs);
+      brk[warp * 64 + i] = make_float2(xr * cs - xi * sn, xi * cs + xr * sn);
+    }
   }
   __syncthreads();
 
@@ -139,28 +161,33 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
   }
 
   // -------------------------------------------------------------- consumers
-  // rotated query for this lane's 16 pairs, pre-multiplied by e^{-j (warp*P) theta} (this warp's first page)
-  float qre[16], qim[16];
-  {
-    const __half* qh = q + ((size_t)b * kv.H + h) * 128;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int i = 16 * c + j;
-      const float f = exp2f(-(float)i * (kLog2Theta / 64.f));
-      const float xr = __half2float(qh[i]), xi = __half2float(qh[i + 64]);
-      float sn, cs; sincosf((float)(seq_len - 1 - warp * P) * f, &sn, &cs);
-      qre[j] = xr * cs - xi * sn;
-      qim[j] = xi * cs + xr * sn;
-    }
-  }
   float m = -5e4f, d = 0.f, zsum = 0.f, acc[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   const int tpl = P >> 3;                                          // tokens per lane per page
+  float2* mybrk = brk + warp * 64 + 16 * c;
 
   for (int pg = warp; pg < npages; pg += DEC_CONSUMERS) {
     const int s = pg % DEC_STAGES;
     const int valid = (pg == npages - 1) ? last_valid : P;
+    // this page's query bracket as half2 couples (j, j+4); then advance the FP32 copy to the warp's next page
+    __half2 qre2[8], qim2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int ja = 8 * (u >> 2) + (u & 3);
+      const float2 a = mybrk[ja], bb = mybrk[ja + 4];
+      qre2[u] = __floats2half2_rn(a.x, bb.x);
+      qim2[u] = __floats2half2_rn(a.y, bb.y);
+    }
+    __syncwarp();
+    if (ts == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 st2 = stepr[16 * c + j], v = mybrk[j];
+        mybrk[j] = make_float2(v.x * st2.x - v.y * st2.y, v.y * st2.x + v.x * st2.y);
+      }
+    }
+    __syncwarp();
     mbar_wait(&full[s], (pg / DEC_STAGES) & 1);
     const uint8_t* st = ring + s * stage_bytes;
     const uint8_t* kblk = st;
@@ -169,10 +196,10 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
     const __half2* vpar = reinterpret_cast<const __half2*>(st + 132 * P);
 
     // ---- scores of this lane's tokens
-    float x[DEC_MAX_TPL];
+    float x[kMaxTpl];
     float xmax = -5e4f;
 #pragma unroll
-    for (int i = 0; i < DEC_MAX_TPL; ++i) {
+    for (int i = 0; i < kMaxTpl; ++i) {
       x[i] = 0.f;
       if (i < tpl) {
         const int tl = ts + 8 * i;
@@ -182,44 +209,43 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
         const bool swp = (ts & 2) != 0;
         const uint2 k_a = *reinterpret_cast<const uint2*>(kr + (swp ? 32 : 0) + c * 8);
         const uint2 k_b = *reinterpret_cast<const uint2*>(kr + (swp ? 0 : 32) + c * 8);
-        const uint2 k_lo = swp ? k_b : k_a;                                    // elements 16c .. 16c+15
-        const uint2 k_hi = swp ? k_a : k_b;                                    // elements 64+16c ..
-        const float2 kp = __half22float2(kpar[tl]);
-        const float4* trow = reinterpret_cast<const float4*>(tab) + tl * 4 + c;
-        float xa = 0.f, xb = 0.f;      // two chains: the 32 fma of a token are no longer one dependent sequence
+        const uint2 k_lo = swp ? k_b : k_a;                                    // elements 16c .. 16c+15   (re)
+        const uint2 k_hi = swp ? k_a : k_b;                                    // elements 64+16c ..       (im)
+        const __half2 kp = kpar[tl];
+        const __half2 ks2 = __half2half2(__low2half(kp)), kz2 = __hneg2(__half2half2(__high2half(kp)));
+        const uint2* trow = tabh + tl * 4 + c;
+        __half2 xa2 = __half2half2(__ushort_as_half(0)), xb2 = xa2;
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float4 t2 = trow[(j >> 1) * P * 4];                          // (cos, sin) of pairs j and j+1
-          const uint32_t wl = (j < 8) ? k_lo.x : k_lo.y, wh = (j < 8) ? k_hi.x : k_hi.y;
-          {
-            const float kre = fmaf(nib_f(wl, j & 7), kp.x, -kp.y), kim = fmaf(nib_f(wh, j & 7), kp.x, -kp.y);
-            const float rr = kre * t2.x - kim * t2.y, ri = kim * t2.x + kre * t2.y;     // zk e^{j t_lo theta}
-            xa = fmaf(qre[j], rr, xa);
-            xa = fmaf(qim[j], ri, xa);
-          }
-          {
-            const float kre = fmaf(nib_f(wl, (j + 1) & 7), kp.x, -kp.y), kim = fmaf(nib_f(wh, (j + 1) & 7), kp.x, -kp.y);
-            const float rr = kre * t2.z - kim * t2.w, ri = kim * t2.z + kre * t2.w;
-            xb = fmaf(qre[j + 1], rr, xb);
-            xb = fmaf(qim[j + 1], ri, xb);
-          }
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t wl = (u < 4) ? k_lo.x : k_lo.y, wh = (u < 4) ? k_hi.x : k_hi.y;
+          const __half2 kre = __hfma2(nib2(wl, u & 3), ks2, kz2), kim = __hfma2(nib2(wh, u & 3), ks2, kz2);
+          const uint2 t = trow[u * P * 4];
+          const __half2 c2 = *reinterpret_cast<const __half2*>(&t.x), s2 = *reinterpret_cast<const __half2*>(&t.y);
+          const __half2 rr = __hfma2(kre, c2, __hneg2(__hmul2(kim, s2)));      // Re(zk e^{j t_lo theta})
+          const __half2 ri = __hfma2(kim, c2, __hmul2(kre, s2));
+          if (u & 1) { xb2 = __hfma2(qre2[u], rr, xb2); xb2 = __hfma2(qim2[u], ri, xb2); }
+          else       { xa2 = __hfma2(qre2[u], rr, xa2); xa2 = __hfma2(qim2[u], ri, xa2); }
         }
-        xa += xb;
-        xa += __shfl_xor_sync(0xffffffffu, xa, 1);
-        xa += __shfl_xor_sync(0xffffffffu, xa, 2);
-        x[i] = xa * kSmScale;
+        const float2 fa = __half22float2(xa2), fb = __half22float2(xb2);
+        float xs = (fa.x + fa.y) + (fb.x + fb.y);
+        xs += __shfl_xor_sync(0xffffffffu, xs, 1);
+        xs += __shfl_xor_sync(0xffffffffu, xs, 2);
+        x[i] = xs * kSmScale;
         if (tl < valid) xmax = fmaxf(xmax, x[i]);
       }
     }
-    // ---- one rescale per page, then p * v with the dequant folded
+    // ---- one rescale per page, then p * v with the dequant folded; V partial sums of the page in half2
     const float m_new = fmaxf(m, xmax);
     const float sc = exp2f(m - m_new);
     m = m_new;
     d *= sc; zsum *= sc;
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] *= sc;
+    __half2 pv[16];
 #pragma unroll
-    for (int i = 0; i < DEC_MAX_TPL; ++i) {
+    for (int u = 0; u < 16; ++u) pv[u] = __half2half2(__ushort_as_half(0));
+#pragma unroll
+    for (int i = 0; i < kMaxTpl; ++i) {
       if (i < tpl) {
         const int tl = ts + 8 * i;
         if (tl < valid) {
@@ -228,23 +254,22 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
           const float p = exp2f(x[i] - m_new);
           d += p;
           zsum = fmaf(p, vp.y, zsum);
-          const float ps = p * vp.x;
+          const __half2 ps2 = __float2half2_rn(p * vp.x);
           const uint32_t w4[4] = {vw.x, vw.y, vw.z, vw.w};
 #pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = fmaf(ps, nib_f(w4[e >> 3], e & 7), acc[e]);
+          for (int u = 0; u < 16; ++u) pv[u] = __hfma2(nib2(w4[u >> 2], u & 3), ps2, pv[u]);
         }
       }
     }
+    // couple u of word w holds elements (8w + q, 8w + q + 4)
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float2 f = __half22float2(pv[u]);
+      acc[8 * (u >> 2) + (u & 3)] += f.x;
+      acc[8 * (u >> 2) + (u & 3) + 4] += f.y;
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
-    // advance the query rotation to this warp's next page
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float2 st2 = stepr[16 * c + j];
-      const float nr = qre[j] * st2.x - qim[j] * st2.y;
-      qim[j] = qim[j] * st2.x + qre[j] * st2.y;
-      qre[j] = nr;
-    }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] -= zsum;      // sum_t p_t z_t is common to all elements of the head
