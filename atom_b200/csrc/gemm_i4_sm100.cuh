@@ -491,11 +491,12 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
 #pragma unroll
           for (int i = 0; i < C::CPT; ++i) {
             acc[i] *= kInv;
-            float a = fabsf(acc[i]), mx = a, mn = a;
-            if (n0 + row >= args.N) { mx = -INFINITY; mn = INFINITY; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
-            if (lane == 0) { xmx[(ewarp & 3) * BN + colbase + i] = mx; xmn[(ewarp & 3) * BN + colbase + i] = mn; }
+            // |v| >= 0: IEEE bit patterns order like unsigned integers, so one REDUX each replaces 5 shuffle rounds
+            uint32_t ua = __float_as_uint(fabsf(acc[i])), umx = ua, umn = ua;
+            if (n0 + row >= args.N) { umx = 0u; umn = 0x7f800000u; }
+            umx = __reduce_max_sync(0xffffffffu, umx);
+            umn = __reduce_min_sync(0xffffffffu, umn);
+            if (lane == 0) { xmx[(ewarp & 3) * BN + colbase + i] = __uint_as_float(umx); xmn[(ewarp & 3) * BN + colbase + i] = __uint_as_float(umn); }
           }
           asm volatile("bar.sync 1, %0;" ::"n"(128 * C::EPI_WGS) : "memory");
           const int n = n0 + row;

@@ -75,10 +75,35 @@ class LinearInt4(nn.Module):
         self.scale_int8.copy_((0.02 / 127 / math.sqrt(k) * 8) * (1 + torch.rand(self.scale_int8.shape, device=dev, generator=g)))
         return self
 
-    def forward(self, input):
+    def forward(self, input, flags=ops.GEMM_AUTO):
         outlier, norms, outlier_scales, norm_scales = input
         f = {"int4": ops.dense_layer_gemm_i4_o4, "fp16": ops.dense_layer_gemm_i4_fp16}[self.out_dtype]
-        return f(norms, self.weight_int4, norm_scales, self.scale_int4, outlier, self.weight_int8, outlier_scales, self.scale_int8)
+        return f(norms, self.weight_int4, norm_scales, self.scale_int4, outlier, self.weight_int8, outlier_scales, self.scale_int8,
+                 flags=flags)
+
+
+def run_concurrently(layers, x):
+    """Decode-sized batches: the GEMMs that share one input (q/k/v, gate/up) are independent and each too small to fill
+    the GPU, so they run side by side on forked streams, un-split along K (a 4096-channel projection is then 32 CTAs);
+    the fork/join is captured into CUDA graphs like any other dependency.  Larger batches run one after the other."""
+    if x[0].shape[0] > 64 or len(layers) == 1:
+        return [l(x) for l in layers]
+    cur = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    outs = [None] * len(layers)
+    side = [torch.cuda.Stream(device=x[0].device) for _ in layers[1:]]
+    for st in side:
+        st.wait_event(ev)
+    outs[0] = layers[0](x, flags=ops.GEMM_NO_SPLITK)
+    for i, st in enumerate(side):
+        with torch.cuda.stream(st):
+            outs[i + 1] = layers[i + 1](x, flags=ops.GEMM_NO_SPLITK)
+    for i, st in enumerate(side):
+        cur.wait_stream(st)
+        for t in (outs[i + 1] if isinstance(outs[i + 1], tuple) else (outs[i + 1],)):
+            t.record_stream(cur)
+    return outs
 
 
 class LlamaMLP(nn.Module):
@@ -93,7 +118,8 @@ class LlamaMLP(nn.Module):
         self.down_proj = LinearInt4(self.intermediate_size, self.hidden_size, out_dtype="fp16")
 
     def forward(self, x):
-        return self.down_proj(ops.activate_fp16_i4(self.gate_proj(x), self.up_proj(x)))
+        gate, up = run_concurrently([self.gate_proj, self.up_proj], x)
+        return self.down_proj(ops.activate_fp16_i4(gate, up))
 
 
 def _dequant_o4(d, d_scale, num_heads):
@@ -129,9 +155,7 @@ class LlamaAttention(nn.Module):
     def forward(self, hidden_states, blen: BatchLenInfo, prefill_kv, decode_kv) -> torch.Tensor:
         nvtx = torch.cuda.nvtx
         nvtx.range_push("qkv_proj")
-        q_proj = self.q_proj(hidden_states)
-        k_proj = self.k_proj(hidden_states)
-        v_proj = self.v_proj(hidden_states)
+        q_proj, k_proj, v_proj = run_concurrently([self.q_proj, self.k_proj, self.v_proj], hidden_states)
         nvtx.range_pop()
         stack = []
         nh, hd = self.num_heads, self.head_dim
