@@ -118,13 +118,18 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: atom_b200 has no CPU path")
+    ref_mode = a.impl == "reference"
+    if ref_mode and world > 1:
+        # the reference has no multi-GPU path: rank 0 alone measures it (single GPU), the other ranks leave at once
+        if rank != 0:
+            return
+        world = 1
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    ref_mode = a.impl == "reference"
     if ref_mode:
         from oracle import ref_gpu as R
         if not R.available():
