@@ -50,7 +50,8 @@ def rotary_pos_emb(q, k, beg):
 
 class LinearInt4(nn.Module):
     """llama.py:35-68.  weight_int4 u8 [out, (in-128)/2], weight_int8 i8 [out, 128], scale_int4 f16 [in/128-1, S(out)],
-    scale_int8 f16 [S(out)] -- the kernels read the first `out` halves of each scale row ([G][N] addressing)."""
+    scale_int8 f16 [S(out)] -- allocated like the reference; the kernels read scale_int4 as a flat [group][out] array
+    (pitch `out`, so only the first (in/128-1)*out halves are live) and the first `out` halves of scale_int8."""
 
     def __init__(self, in_features, out_features, out_dtype, bias=False):
         super().__init__()

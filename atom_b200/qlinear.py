@@ -88,29 +88,39 @@ class QLinearLayer(nn.Module):
         return
 
     @torch.no_grad()
-    def pack(self, device=None):
-        """Real-INT4 operands from the (reordered, un-fake-quantised if available) weight.  Requires the W4A4 recipe:
-        wbits=4, symmetric, weight_group_size=128, keeper=128 with INT8 precision."""
+    def int4_operands(self):
+        """Real-INT4 GEMM operands (CPU tensors) of the (reordered, un-fake-quantised if available) weight, without
+        changing the layer.  Requires the W4A4 recipe: wbits=4, symmetric, weight_group_size=128, keeper=128 (INT8)."""
         a = self.args
-        assert a.wbits == 4 and a.w_sym and a.weight_group_size == 128 and a.keeper == 128, "pack() implements the W4A4/g128/keeper128 recipe"
-        w = (self._w_unquantized if self._w_unquantized is not None else self.weight).float()
+        assert a.wbits == 4 and a.w_sym and a.weight_group_size == 128 and a.keeper == 128 and a.weight_channel_group == 2, "pack() implements the W4A4/g128/keeper128 recipe"
+        w = (self._w_unquantized if self._w_unquantized is not None else self.weight).float().cpu()
         out_f, in_f = w.shape
         assert in_f % 128 == 0 and in_f >= 256 and out_f % 8 == 0
         keep = w[:, -128:].contiguous()
         body = w[:, :-128].contiguous()
         # keeper: INT8 per output row; body: INT4 per (group, channel pair); same arithmetic as quant()
+        # The GEMM (like the reference's, Dense_layer_gemm_i4_o16.cuh:404-434) reads EVERY weight scale -- the keeper's
+        # too -- from column n&~1 for activation rows with m%16 < 8 and from n|1 otherwise, so scales must be shared by
+        # adjacent output channels to be applied correctly: the INT4 body is (weight_channel_group = 2), and the
+        # keeper is exported with one INT8 scale per channel pair for the same reason.
         ks = keep.abs().amax(dim=-1, keepdim=True).clamp(min=1e-5) / 127
+        ks = ks.view(out_f // 2, 2).amax(dim=1, keepdim=True).repeat_interleave(2, dim=0)
         kq = torch.clamp(torch.round(keep / ks), -128, 127).to(torch.int8)
         # quant() quantises the body with the keeper columns zeroed: the last group is all zero there and lives in the
         # keeper instead, so only the first in/128-1 groups are packed
         q, scale = quantize_weight_int(body, 4, 128, True, a.weight_channel_group, a.w_clip_ratio)
         qi = q.to(torch.int16)
         packed = ((qi[:, 0::2] & 0xF) | ((qi[:, 1::2] & 0xF) << 4)).to(torch.uint8)
+        return {"weight_int4": packed.contiguous(), "weight_int8": kq.contiguous(),
+                "scale_int4": scale.to(torch.float16).contiguous(), "scale_int8": ks.reshape(-1).to(torch.float16).contiguous()}
+
+    @torch.no_grad()
+    def pack(self, device=None):
+        """Switch this layer to the real-INT4 kernels: registers int4_operands() as buffers on `device`; forward() then
+        runs reorder_fp16_i4 + dense_layer_gemm_i4_fp16 (CUDA only)."""
         dev = device if device is not None else self.weight.device
-        self.register_buffer("weight_int4", packed.contiguous().to(dev))
-        self.register_buffer("weight_int8", kq.contiguous().to(dev))
-        self.register_buffer("scale_int4", scale.to(torch.float16).contiguous().to(dev))
-        self.register_buffer("scale_int8", ks.reshape(-1).to(torch.float16).contiguous().to(dev))
-        self.register_buffer("identity_index", torch.arange(in_f, dtype=torch.int16, device=dev))
+        for k, v in self.int4_operands().items():
+            self.register_buffer(k, v.to(dev))
+        self.register_buffer("identity_index", torch.arange(self.weight.shape[1], dtype=torch.int16, device=dev))
         self.packed = True
         return self
