@@ -40,6 +40,8 @@ class KvPoolInt4:
         return len(self._free)
 
     def alloc_block(self) -> int:
+        if not self._free:
+            raise RuntimeError("KvPoolInt4: out of pages (capacity %d)" % self._buf.size(0))
         return self._free.pop()
 
     def free_block(self, idx: int):

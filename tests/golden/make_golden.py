@@ -4,7 +4,8 @@ Two sources, both the reference's own code, neither copied into this repo:
   * the CPU golden functions of test_Reorder.cu / test_RMSNorm.cu / test_activate.cu
     (compiled where they lie, see gen_ref_golden.cu);
   * model/quant.py + model/qLinearLayer.py imported from /root/reference/model with
-    `bitsandbytes` stubbed (only used for --quant_type fp, quant.py:134-138).
+    `bitsandbytes` stubbed (only used for --quant_type fp, quant.py:134-138);
+  * generate_request_set of e2e/punica-atom/benchmarks/bench_textgen.py (the serving harness's workload).
 Run:  python tests/golden/make_golden.py
 """
 import os, subprocess, sys, types, tempfile
@@ -79,6 +80,20 @@ def python_golden():
     print("wrote python fake-quant golden")
 
 
+def request_set_golden():
+    """generate_request_set of the reference's serving harness (benchmarks/bench_textgen.py:31-47), imported as is."""
+    import importlib
+    sys.path.insert(0, os.path.join(REF, "e2e/punica-atom"))
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())          # keep this repo's own top-level modules out of the way
+    m = importlib.import_module("benchmarks.bench_textgen")
+    os.chdir(cwd)
+    a, b = m.generate_request_set(160, 2048), m.generate_request_set(48, 512)
+    np.savez_compressed(os.path.join(HERE, "ref_py_request_set.npz"), p160=a.prompt_lens, o160=a.output_lens,
+                        p48=b.prompt_lens, o48=b.output_lens)
+    print("wrote request-set golden")
+
+
 if __name__ == "__main__":
     cpp_golden("reorder", 21, 4096)
     # test_RMSNorm.cu does not compile against the reference's own RMSNorm.cu (its perf_gpu() instantiates
@@ -87,3 +102,4 @@ if __name__ == "__main__":
     # float64 restatement in the tests, and the reference CUDA kernel on the GPU box.
     cpp_golden("activate", 5, 11008)
     python_golden()
+    request_set_golden()
