@@ -1,10 +1,25 @@
 #!/bin/bash
-# One GPU visit: environment, micro-benchmarks, GEMM probes, the gpu test suite, timing.  Everything lands in gpurun_out/.
+# One GPU visit (1 GPU): everything a round needs, each step under its own timeout, everything into gpurun_out/.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [steps...]'
+# steps (default: all): tests smoke bench gtime trace layer harness micro
 set -u
 mkdir -p gpurun_out
 OUT=gpurun_out
+STEPS=${*:-tests smoke bench gtime trace layer harness micro}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/smi.txt 2>&1
-echo "== microbench" ; timeout 120 ./tools/microbench > $OUT/microbench.jsonl 2>&1; echo "rc=$?"; tail -40 $OUT/microbench.jsonl
-echo "== diag" ; timeout 300 python tools/gpu_check.py diag > $OUT/diag.jsonl 2> $OUT/diag.err; echo "rc=$?"; cat $OUT/diag.jsonl | cut -c1-400; tail -5 $OUT/diag.err
-echo "== pytest" ; timeout 1500 python -m pytest tests -m gpu -q --timeout=240 -x -p no:cacheprovider > $OUT/pytest.txt 2>&1; echo "rc=$?"; tail -40 $OUT/pytest.txt
-echo "== timing" ; timeout 600 python tools/gpu_check.py time > $OUT/timing.jsonl 2> $OUT/timing.err; echo "rc=$?"; cat $OUT/timing.jsonl; tail -5 $OUT/timing.err
+for s in $STEPS; do case $s in
+  tests)   echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider > $OUT/pytest.txt 2>&1; echo "rc=$?"; tail -15 $OUT/pytest.txt ;;
+  smoke)   echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
+  bench)   echo "== bench ours"; timeout 600 python bench.py 2> $OUT/bench.err | tee $OUT/bench_ours.json; tail -3 $OUT/bench.err
+           echo "== bench reference"; timeout 600 python bench.py --impl reference 2> $OUT/bench_ref.err | tee $OUT/bench_ref.json; tail -3 $OUT/bench_ref.err ;;
+  gtime)   echo "== GEMM graph timing"; timeout 600 python tools/gpu_check.py gtime 2> $OUT/gtime.err | tee $OUT/gtime.jsonl; tail -3 $OUT/gtime.err
+           echo "== decode-shape table"; timeout 600 python tools/gpu_check.py gshape 2>> $OUT/gtime.err | tee $OUT/gshape.jsonl ;;
+  trace)   echo "== pipeline trace"; : > $OUT/trace.jsonl
+           for cfg in "16 0" "16 1" "4096 2"; do timeout 120 python tools/gpu_check.py trace $cfg 2>&1 | tail -1 | tee -a $OUT/trace.jsonl | cut -c1-2500; done ;;
+  layer)   echo "== decoder-layer decode step"
+           timeout 300 python tools/layer_bench.py 2>&1 | tail -1 | tee $OUT/layer_7b.json
+           timeout 300 python tools/layer_bench.py --hidden 5120 --inter 13824 --heads 40 --batch 32 --kvlen 1024 --layers 40 2>&1 | tail -1 | tee $OUT/layer_13b.json ;;
+  harness) echo "== continuous-batching harness"; timeout 900 python tools/bench_textgen.py --model 7b --batch-size 16 --num-batches 2 --maxlen 512 2> $OUT/textgen.err | tee $OUT/textgen_7b.txt | tail -9; tail -3 $OUT/textgen.err ;;
+  micro)   echo "== microbenchmarks"; for b in microbench sync_bench tma_bench tmem_bench; do timeout 120 ./tools/$b > $OUT/$b.jsonl 2>&1; echo "$b rc=$?"; done ;;
+  *) echo "unknown step $s" ;;
+esac; done
