@@ -189,17 +189,21 @@ if __name__ == "__main__":
         diag()
     elif cmd == "gtime":
         gtiming([int(x) for x in sys.argv[2:]] or [16, 32, 64, 128, 256, 1024, 4096])
-    elif cmd == "gshape":      # gshape M N K : compare split-K factors on one shape
-        m, n, k = [int(x) for x in sys.argv[2:5]]
-        base = O.make_gemm_inputs(m, n, k, seed=1)
-        per_set = sum(x.nbytes for x in base)
-        nrot = max(3, int(300e6 // per_set) + 1)
-        sets = [[T(x) for x in base] for _ in range(nrot)]
-        rec = {"gshape": [m, n, k]}
-        for name, flags in {"auto": 0, "nosplit": 1, "split2": 16, "split4": 32}.items():
-            us = graph_time(lambda i: ops.dense_layer_gemm_i4_fp16(*sets[i % nrot], flags=flags), nrot, launches=nrot)
-            rec[name] = round(us, 2)
-        print(json.dumps(rec), flush=True)
+    elif cmd == "gshape":      # gshape [M N K] : compare split-K factors on one shape (default: the Llama-7B/13B decode shapes)
+        shapes = [tuple(int(x) for x in sys.argv[2:5])] if len(sys.argv) >= 5 else [
+            (16, 4096, 4096), (16, 11008, 4096), (16, 4096, 11008), (32, 5120, 5120), (32, 13824, 5120), (32, 5120, 13824),
+            (64, 4096, 4096)]
+        for m, n, k in shapes:
+            base = O.make_gemm_inputs(m, n, k, seed=1)
+            per_set = sum(x.nbytes for x in base)
+            nrot = max(3, int(300e6 // per_set) + 1)
+            sets = [[T(x) for x in base] for _ in range(nrot)]
+            rec = {"gshape": [m, n, k]}
+            for name, flags in {"auto": 0, "nosplit": 1, "split2": 16, "split4": 32}.items():
+                us = graph_time(lambda i: ops.dense_layer_gemm_i4_fp16(*sets[i % nrot], flags=flags), nrot, launches=nrot)
+                rec[name] = round(us, 2)
+            print(json.dumps(rec), flush=True)
+            del sets
     elif cmd == "trace":
         trace(int(sys.argv[2]), int(sys.argv[3]))
     elif cmd == "time":
