@@ -27,7 +27,7 @@ class _FakeLM:
         self.calls = []
 
     def __call__(self, ids, blen, prefill_kv, decode_kv):
-        assert ids.dtype == torch.long and ids.numel() == blen.doff + blen.decode
+        assert ids.dtype in (torch.long, torch.int32) and ids.numel() == blen.doff + blen.decode
         assert len(blen.prefills) + blen.decode <= self.batch_size
         assert (prefill_kv is None) == (len(blen.prefills) == 0) and (decode_kv is None) == (blen.decode == 0)
         if prefill_kv is not None:      # page table of the prompts: enough pages, last page offset consistent with the length
@@ -35,11 +35,12 @@ class _FakeLM:
             for plen, pages, last in zip(blen.prefills, n_pages, prefill_kv.last_page_offset.tolist()):
                 assert pages == -(-plen // self.block_len) and last == (plen - 1) % self.block_len + 1
         if decode_kv is not None:
-            assert decode_kv.indptr.numel() == blen.decode + 1 and decode_kv.indicies.numel() == int(decode_kv.indptr[-1])
-            assert len(set(decode_kv.indicies.tolist())) == decode_kv.indicies.numel()       # no page shared
+            nnz = int(decode_kv.indptr[-1])          # a static (graph) page table is over-allocated: only the first nnz count
+            assert decode_kv.indptr.numel() == blen.decode + 1 and decode_kv.indicies.numel() >= nnz
+            assert len(set(decode_kv.indicies[:nnz].tolist())) == nnz                          # no page shared
         self.calls.append((list(blen.prefills), blen.decode, None if decode_kv is None else
                            ((decode_kv.indptr[1:] - decode_kv.indptr[:-1] - 1) * self.block_len + decode_kv.last_page_offset).tolist()))
-        nxt = (ids * 7 + 3) % self.vocab
+        nxt = (ids.long() * 7 + 3) % self.vocab
         return torch.nn.functional.one_hot(nxt, self.vocab).float(), None
 
 
@@ -83,3 +84,24 @@ def test_admission_waits_for_pages_and_reports_impossible_requests():
         tg.run_textgen(lm, rs, tg.TextGenConfig(3), tiny, torch.device("cpu"))
     with pytest.raises(RuntimeError, match="out of pages"):
         [tiny.alloc_block() for _ in range(3)]
+
+
+def test_decode_graph_runner_static_buffers_equal_the_eager_page_tables():
+    """DecodeGraphRunner with capture=False: same packed int32 buffer, same model calls, no CUDA graph -- the host logic
+    of the graphed decode path.  Tokens, step count and page accounting must equal the plain loop's."""
+    rs = tg.generate_request_set(11, 80)
+    block, bs = 16, 4
+    outs = []
+    for use_runner in (False, True):
+        pool = KvPoolInt4(1, 2, 128, tg.pool_capacity(bs, 80, block), block, torch.device("cpu"))
+        lm = _FakeLM(97, bs, block)
+        runner = tg.DecodeGraphRunner(lm, pool, "cpu", max_pages_per_seq=80 // block + 1, capture=False) if use_runner else None
+        res = tg.run_textgen(lm, rs, tg.TextGenConfig(bs), pool, torch.device("cpu"), keep_tokens=True, decode_runner=runner)
+        outs.append((res.tokens, res.steps, [(c[0], c[1], c[2]) for c in lm.calls], res.graphed_steps))
+        assert pool.num_free_blocks == tg.pool_capacity(bs, 80, block)
+    assert outs[0][:3] == outs[1][:3]                     # identical tokens, steps and per-step (prefills, decode, kv lengths)
+    assert outs[0][3] == 0 and 0 < outs[1][3] < outs[1][1]
+    with pytest.raises(RuntimeError, match="sized for"):
+        pool = KvPoolInt4(1, 2, 128, 64, block, torch.device("cpu"))
+        tg.run_textgen(_FakeLM(97, bs, block), rs, tg.TextGenConfig(bs), pool, torch.device("cpu"),
+                       decode_runner=tg.DecodeGraphRunner(_FakeLM(97, bs, block), pool, "cpu", max_pages_per_seq=1, capture=False))

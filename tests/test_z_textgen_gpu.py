@@ -6,7 +6,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(seed_pages):
+def _run(seed_pages, graphs=False):
     from atom_b200 import textgen as tg
     from atom_b200.kvcache import KvPoolInt4
     from atom_b200.llama import LinearInt4, LlamaConfig, LlamaForCausalLM
@@ -26,7 +26,10 @@ def _run(seed_pages):
     for _ in range(seed_pages):            # shift the page ids the requests will get
         pool.alloc_block()
     free0 = pool.num_free_blocks
-    res = tg.run_textgen(model.eval(), rs, tg.TextGenConfig(3), pool, dev, sync=torch.cuda.synchronize, keep_tokens=True)
+    runner = tg.DecodeGraphRunner(model.eval(), pool, dev, max_pages_per_seq=72 // 16 + 1) if graphs else None
+    res = tg.run_textgen(model.eval(), rs, tg.TextGenConfig(3), pool, dev, sync=torch.cuda.synchronize, keep_tokens=True,
+                         decode_runner=runner)
+    assert (res.graphed_steps > 0) == graphs
     assert pool.num_free_blocks == free0
     assert [len(t) for t in res.tokens] == rs.output_lens.tolist()
     assert all(0 <= t < 128 for toks in res.tokens for t in toks)
@@ -38,3 +41,8 @@ def test_textgen_harness_end_to_end_and_page_placement_independent():
     a = _run(0)
     b = _run(5)          # same requests on different physical pages: greedy tokens must not change
     assert a == b
+
+
+@pytest.mark.timeout(300)
+def test_textgen_decode_steps_from_cuda_graphs_give_the_same_tokens():
+    assert _run(0, graphs=True) == _run(0)

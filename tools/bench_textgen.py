@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--layers", type=int, default=0, help="override the number of decoder layers (0 = the model's)")
     ap.add_argument("--block-len", type=int, default=32)
+    ap.add_argument("--no-cuda-graphs", action="store_true", help="run decode-only steps eagerly too (the reference's way)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_textgen: needs a CUDA device (the INT4 kernels have no CPU path)")
@@ -58,7 +59,9 @@ def main():
     cfg = tg.TextGenConfig(args.batch_size)
     pool = KvPoolInt4(layers, mc.num_heads, mc.hidden_size // mc.num_heads,
                       tg.pool_capacity(args.batch_size, args.maxlen, args.block_len), args.block_len, device)
-    res = tg.run_textgen(model, rs, cfg, pool, device, sync=torch.cuda.synchronize)
+    runner = None if args.no_cuda_graphs else tg.DecodeGraphRunner(
+        model, pool, device, max_pages_per_seq=(args.maxlen + args.block_len - 1) // args.block_len + 1)
+    res = tg.run_textgen(model, rs, cfg, pool, device, sync=torch.cuda.synchronize, decode_runner=runner)
     rep = tg.report(rs, cfg, res)
     e, et, d = rep["encode_latency_ms_per_request"], rep["encode_latency_ms_per_token"], rep["decode_latency_ms_per_token"]
     print("num_requests:", rep["num_requests"])
