@@ -170,3 +170,41 @@ def test_exported_attention_projections_stage_by_stage():
     r = O.reorder_fp16_i4(_np(attn), _np(real.self_attn.reorder_index))
     rdq = _check_quant_stage(r, _np(q.self_attn.act_quant(torch.index_select(attn.float(), 1, q.self_attn.reorder_index))), "reorder+quant")
     _check_gemm_stage(_gemm(r, real.self_attn.o_proj), rdq, real.self_attn.o_proj, q.self_attn.o_proj, "o_proj")
+
+
+def test_int4_checkpoint_round_trip(tmp_path):
+    """export -> save -> load: every operand identical, config and metadata preserved, wrong files refused."""
+    from atom_b200.checkpoint import load_int4, save_int4
+    from atom_b200.llama import LlamaDecoderLayer
+    q, a = _build(seed=3)
+    real = int4_decoder_layer(q, device=None, layer_idx=2)
+    path = str(tmp_path / "layer.safetensors")
+    save_int4(real, path, extra={"source": "toy", "w_clip_ratio": a.w_clip_ratio})
+    back, extra = load_int4(path, device="cpu")
+    assert isinstance(back, LlamaDecoderLayer) and back.self_attn.layer_idx == 2 and extra["source"] == "toy"
+    sd0, sd1 = real.state_dict(), back.state_dict()
+    assert sd0.keys() == sd1.keys() and len(sd0) == 7 * 4 + 2 * 2 + 1
+    for k in sd0:
+        assert sd0[k].dtype == sd1[k].dtype and torch.equal(sd0[k], sd1[k]), k
+    assert not any(p.is_meta for p in back.parameters())
+    assert back.input_layernorm.variance_epsilon == real.input_layernorm.variance_epsilon
+    # a foreign safetensors file is refused by its format tag
+    from safetensors.torch import save_file
+    other = str(tmp_path / "other.safetensors")
+    save_file({"x": torch.zeros(2)}, other)
+    import pytest
+    with pytest.raises(ValueError, match="not an atom_b200"):
+        load_int4(other, device="cpu")
+
+
+def test_int4_checkpoint_full_model(tmp_path):
+    from atom_b200.checkpoint import load_int4, save_int4
+    from atom_b200.llama import LinearInt4, LlamaConfig, LlamaForCausalLM
+    m = LlamaForCausalLM(LlamaConfig(hidden_size=256, intermediate_size=512, num_attention_heads=2, num_hidden_layers=2, vocab_size=64))
+    for i, lin in enumerate(x for x in m.modules() if isinstance(x, LinearInt4)):
+        lin.init_random(i)
+    path = str(tmp_path / "model.safetensors")
+    save_int4(m, path)
+    back, _ = load_int4(path, device="cpu")
+    assert back.model.config.num_hidden_layers == 2 and back.model.layers[1].self_attn.layer_idx == 1
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), back.state_dict().values()))
