@@ -61,3 +61,68 @@ def quantize_model_llama(layers, args):
             q.quant()
         layers[i] = m
     return layers
+
+
+# ------------------------------------------------------------------------------------------------ Mixtral
+# /root/reference/model/modelutils_mixtral.py:14-150.  Differences from Llama the reference has, kept: q/k/v all take
+# k_proj's input order; every expert shares expert 0's orders (w1/w3 input = experts.0.w1.input, w1/w3 output = w2 input =
+# experts.0.w2.input) and so do the router and post_attention_layernorm; quantisers are assigned as plain callables; the
+# router is never quantised.
+_T6 = "layers.{}.{}.{}.{}.{}.{}"  # layers.10.block_sparse_moe.experts.0.w1.input
+
+
+def _wrap_mixtral(layer, args):
+    from .qmixtral import QMixtralDecoderLayer
+    return layer if isinstance(layer, QMixtralDecoderLayer) else QMixtralDecoderLayer(layer, args)
+
+
+@torch.no_grad()
+def reorder_model_mixtral(layers, args, reorder_index):
+    assert reorder_index is not None, "Reorder index is None"
+    for i in range(len(layers)):
+        m = _wrap_mixtral(layers[i], args)
+        qkv = reorder_index[_T4.format(i, "self_attn", "k_proj", "input")]
+        o_in = reorder_index[_T4.format(i, "self_attn", "o_proj", "input")]
+        m.input_layernorm.register_buffer("reorder_index", qkv)
+        for p in ("q_proj", "k_proj", "v_proj"):
+            getattr(m.self_attn, p).reorder(qkv, None)
+        m.self_attn.o_proj.reorder(o_in, None)
+        m.self_attn.register_buffer("reorder_index", o_in)
+        w1_in = reorder_index[_T6.format(i, "block_sparse_moe", "experts", 0, "w1", "input")]
+        w2_in = reorder_index[_T6.format(i, "block_sparse_moe", "experts", 0, "w2", "input")]
+        m.block_sparse_moe.gate.reorder(w1_in, None)
+        for expert in m.block_sparse_moe.experts:
+            expert.w1.reorder(w1_in, w2_in)
+            expert.w3.reorder(w1_in, w2_in)
+            expert.w2.reorder(w2_in, None)
+        m.post_attention_layernorm.register_buffer("reorder_index", w1_in)
+        layers[i] = m
+    return layers
+
+
+@torch.no_grad()
+def add_act_quant_wrapper_mixtral(layers, args, scales=None):
+    act = partial(quantize_activation_wrapper, args=args)
+    for i in range(len(layers)):
+        m = _wrap_mixtral(layers[i], args)
+        m.self_attn.act_quant = act
+        m.self_attn.v_quant = partial(quantize_attn_v_wrapper, args=args)
+        m.self_attn.k_quant = partial(quantize_attn_k_wrapper, args=args)
+        for expert in m.block_sparse_moe.experts:
+            expert.act_quant = act
+        m.act_quant = act
+        m.block_sparse_moe.act_quant = act
+        layers[i] = m
+    return layers
+
+
+@torch.no_grad()
+def quantize_model_mixtral(layers, args):
+    for i in range(len(layers)):
+        m = _wrap_mixtral(layers[i], args)
+        for expert in m.block_sparse_moe.experts:
+            expert.quant()
+        for p in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            getattr(m.self_attn, p).quant()
+        layers[i] = m
+    return layers

@@ -143,3 +143,28 @@ def test_qmixtral_layer_surface():
     assert q.block_sparse_moe.gate.enable_quant is False          # router stays FP (qMixtralLayer.py:289)
     assert len(q.block_sparse_moe.experts) == 4 and hasattr(q.block_sparse_moe.experts[0], "act_quant")
     assert hasattr(q, "act_quant") and hasattr(q.self_attn, "k_quant")
+
+
+def test_mixtral_drivers_reorder_is_function_preserving_and_router_stays_fp():
+    from atom_b200 import modelutils
+    from atom_b200.qmixtral import ToyMixtralDecoderLayer
+    torch.manual_seed(2)
+    a = _args(kv_cache=True)
+    base = ToyMixtralDecoderLayer(hidden=256, inter=256, heads=2, kv_heads=1, experts=4, top_k=2)
+    x = torch.randn(1, 6, 256)
+    y_fp = base(x)[0]
+    idx = {"layers.0.self_attn.k_proj.input": torch.randperm(256), "layers.0.self_attn.o_proj.input": torch.randperm(256),
+           "layers.0.block_sparse_moe.experts.0.w1.input": torch.randperm(256),
+           "layers.0.block_sparse_moe.experts.0.w2.input": torch.randperm(256)}
+    layers = modelutils.reorder_model_mixtral([base], a, idx)
+    q = layers[0]
+    assert torch.allclose(q(x)[0], y_fp, atol=1e-4)              # a permutation applied consistently changes nothing
+    gate_w = q.block_sparse_moe.gate.weight.clone()
+    modelutils.quantize_model_mixtral(layers, a)
+    assert torch.equal(q.block_sparse_moe.gate.weight, gate_w)    # router untouched (modelutils_mixtral.py:139-145)
+    assert not torch.equal(q.block_sparse_moe.experts[0].w1.weight, q.block_sparse_moe.experts[0].w1._w_unquantized)
+    modelutils.add_act_quant_wrapper_mixtral(layers, a)
+    y4, router = q(x, output_router_logits=True)
+    assert torch.isfinite(y4).all() and router.shape == (6, 4)
+    # the router saw un-quantised activations: its logits equal gate(post_attention_layernorm(h)) of the FP hidden state
+    assert (y4 - y_fp).abs().max() < 0.6 * y_fp.abs().max() and not torch.allclose(y4, y_fp, atol=1e-4)
