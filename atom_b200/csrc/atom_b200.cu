@@ -9,8 +9,10 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <set>
 #include <string>
 #include <unordered_map>
+#include <utility>
 
 #include "../../include/atom_b200.h"
 #include "gemm_i4_sm100.cuh"
@@ -42,6 +44,23 @@ int check_launch(const char* what) {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): raise it once for each pair, under a lock
+// (the reference calls cudaFuncSetAttribute on every launch, GEMM.cuh:757).
+template <typename F>
+int ensure_dynamic_smem(F* func, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(ATOM_E_CUDA, "%s: no current CUDA device", what);
+  const std::pair<const void*, int> key(reinterpret_cast<const void*>(func), dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(key)) return ATOM_OK;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return fail(ATOM_E_CUDA, "%s: cudaFuncSetAttribute(smem=%d): %s", what, bytes, cudaGetErrorString(e));
+  done.insert(key);
+  return ATOM_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ TMA descriptors
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -112,19 +131,14 @@ template <bool kSwap, int BN, int GS, int kPack, int kSplit, bool kO4, int kConv
 int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
   using C = atom::GemmCfg<kSwap, BN, GS, kPack, kSplit, kO4, kConvWarps, kEpiWgs>;
   auto kern = atom::gemm_i4_kernel<kSwap, BN, GS, kPack, kSplit, kO4, kConvWarps, kEpiWgs>;
-  static bool attr_set = false;   // per instantiation; benign race (idempotent)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return fail(ATOM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4");
+  if (rc) return rc;
   const uint64_t kp = (uint64_t)(op.K - 128) / 2;
   // MMA-M operand = kSwap ? weights : tokens
   const void* p4 = kSwap ? op.b : op.a;  const void* q4 = kSwap ? op.a : op.b;
   const void* p8 = kSwap ? op.bk : op.ak; const void* q8 = kSwap ? op.ak : op.bk;
   const uint64_t prow = kSwap ? op.N : op.M, qrow = kSwap ? op.M : op.N;
   CUtensorMap tp4, tq4, tp8, tq8;
-  int rc;
   if ((rc = make_map(&tp4, p4, kp, prow, kp, 64, C::BM, false))) return rc;
   if ((rc = make_map(&tq4, q4, kp, qrow, kp, 64, BN, false))) return rc;
   if ((rc = make_map(&tp8, p8, 128, prow, 128, 128, C::BM, true))) return rc;
@@ -217,8 +231,7 @@ int atom_reorder_fp16_i4(const void* hidden, const void* reorder_index, int seq_
   int rc = quant_check("reorder_fp16_i4", seq_len, hidden_dim, o_outliers, o_norms, outlier_scales, norm_scales);
   if (rc) return rc;
   ATOM_REQUIRE(hidden && reorder_index && aligned16(hidden), "reorder_fp16_i4: null or misaligned input");
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(atom::reorder_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072); attr_set = true; }
+  if ((rc = ensure_dynamic_smem(atom::reorder_quant_kernel, 65536 * 2, "reorder_fp16_i4"))) return rc;   // one fp16 row, hidden <= 65536
   atom::reorder_quant_kernel<<<seq_len, atom::QUANT_THREADS, (size_t)hidden_dim * 2, (cudaStream_t)stream>>>(
       (const __half*)hidden, (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms,
       (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
@@ -232,8 +245,7 @@ int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, cons
   if (rc) return rc;
   ATOM_REQUIRE(hidden && weight && reorder_index && aligned16(hidden) && aligned16(weight), "rmsnorm_fp16_i4: null or misaligned input");
   ATOM_REQUIRE(hidden_dim <= 32768, "rmsnorm_fp16_i4: hidden_dim=%d > 32768 unsupported", hidden_dim);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(atom::rmsnorm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 * 2 / 2 + 65536 + 512); attr_set = true; }
+  if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel, 32768 * 4 + 512, "rmsnorm_fp16_i4"))) return rc;   // row + weight (fp16) + reduction scratch
   atom::rmsnorm_quant_kernel<<<seq_len, atom::QUANT_THREADS, (size_t)hidden_dim * 4 + 512, (cudaStream_t)stream>>>(
       (const __half*)hidden, (const __half*)weight, eps, (const int16_t*)reorder_index, seq_len, hidden_dim,
       (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
@@ -287,11 +299,10 @@ int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, const void
                   (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
   const size_t smem = (size_t)atom::DEC_STAGES * (136 * page_size) + (size_t)8 * page_size * 4 * 8 + 64 * 8 + 4 * 64 * 8 +
                       4 * 4 * 34 * 4 + 2 * atom::DEC_STAGES * 8 + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(atom::batch_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(atom::batch_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
+  if (page_size <= 32) {
+    if ((rc = ensure_dynamic_smem(atom::batch_decode_kernel<4>, 100 * 1024, "batch_decode_i4"))) return rc;
+  } else {
+    if ((rc = ensure_dynamic_smem(atom::batch_decode_kernel<8>, 100 * 1024, "batch_decode_i4"))) return rc;
   }
   if (page_size <= 32)
     atom::batch_decode_kernel<4><<<dim3(batch_size, num_heads), atom::DEC_THREADS, smem, (cudaStream_t)stream>>>((__half*)o, (const __half*)q, kv);
