@@ -28,6 +28,10 @@ sys.path.insert(0, ROOT)
 
 L2_BYTES = 126e6
 
+# the reference's published bench_gemm_i4_o16 numbers (RTX 4090, figures/bench_gemm.png), TOP/s by M
+PUBLISHED_TOPS = {16: 20.079, 32: 38.334, 64: 78.997, 128: 151.281, 256: 312.242, 512: 546.035, 1024: 630.779,
+                  2048: 713.778, 4096: 772.992}
+
 
 def algorithmic_bytes(m, n, k):
     """packed operands + keepers + scales + FP16 output, per launch."""
@@ -298,12 +302,15 @@ def main():
                 "peak_source": "2 x measured bf16 cuBLAS burst (INT8 tcgen05 = 2x bf16 rate; Blackwell has no INT4 MMA)"}
     line = {
         "metric": "gemm_i4_o16_throughput", "value": value, "unit": "TOP/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s4 x s4 -> s32 (via tcgen05 kind::i8), fp16 out",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": (value / PUBLISHED_TOPS[M]) if M in PUBLISHED_TOPS else None, "dtype": "s4 x s4 -> s32 (via tcgen05 kind::i8), fp16 out",
         "data": "synthetic", "impl": a.impl,
         "config": {"workload": f"gemm_i4_o16 M={M} N={N} K={K} (K incl. 128 INT8 keeper) group_size=128", "gemms_per_step": R_sets,
                    "l2": f"{R_sets} distinct operand sets per step = {R_sets * per_set / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
                    "launch": "one CUDA graph replay per step" if graph is not None else "python loop on the legacy stream (reference launcher)",
-                   "parallelism": f"dp{world} (independent GEMM problems per rank, no collective)"},
+                   "parallelism": f"dp{world} (independent GEMM problems per rank, no collective)",
+                   "published_baseline": (f"{PUBLISHED_TOPS[M]} TOP/s on one RTX 4090 (BASELINE.md section 1, bench_gemm.png)"
+                                          if M in PUBLISHED_TOPS else None)},
         "e2e": {"value": e2e_tops, "unit": "TOP/s", "h2d_bytes_per_step": act_bytes, "d2h_bytes_per_step": M * N * 2,
                 "steps": e2e_steps, "note": "one GEMM per step: pinned H2D of the activation tuple, op, D2H of D, stream sync" + ("" if ref_mode else "; the three nodes replayed from one CUDA graph")},
         "gpu_launches": a.steps * R_sets + e2e_steps + 5,
