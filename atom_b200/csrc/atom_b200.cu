@@ -16,6 +16,7 @@
 
 #include "../../include/atom_b200.h"
 #include "gemm_i4_sm100.cuh"
+#include "gemm_f16path_sm100.cuh"
 #include "kv_kernels.cuh"
 #include "quant_kernels.cuh"
 
@@ -160,9 +161,35 @@ int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
   return ATOM_OK;
 }
 
+// EXPERIMENTAL FP16-path kernel (gemm_f16path_sm100.cuh): prefill-sized o16 GEMMs only, opt-in through ATOM_GEMM_FP16_PATH.
+template <int BN, int kPack, int kRing, int kConvWarps>
+int launch_gemm_f16path(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
+  using C = atom::F16Cfg<BN, kPack, kRing, kConvWarps>;
+  auto kern = atom::gemm_w4a4_f16path_kernel<BN, kPack, kRing, kConvWarps>;
+  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (fp16 path)");
+  if (rc) return rc;
+  const uint64_t kp = (uint64_t)(op.K - 128) / 2;
+  CUtensorMap ta4, tb4, ta8, tb8;
+  if ((rc = make_map(&ta4, op.a, kp, op.M, kp, 64, C::BM, false))) return rc;
+  if ((rc = make_map(&tb4, op.b, kp, op.N, kp, 64, BN, false))) return rc;
+  if ((rc = make_map(&ta8, op.ak, 128, op.M, 128, 64, C::BM, false))) return rc;
+  if ((rc = make_map(&tb8, op.bk, 128, op.N, 128, 64, BN, false))) return rc;
+  const dim3 grid((unsigned)((op.N + BN - 1) / BN), (unsigned)((op.M + C::BM - 1) / C::BM), 1);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(ta4, tb4, ta8, tb8, args);
+  return check_launch("gemm_i4 (fp16 path)");
+}
+
 template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
+  if constexpr (!kO4) {
+    if (!skinny && (flags & ATOM_GEMM_FP16_PATH)) {
+      // 128 x 256 tiles once they fill the machine (converter work per MMA cycle halves), 128 x 128 below
+      const int64_t tiles256 = ((op.M + 127) / 128) * ((op.N + 255) / 256);
+      return tiles256 >= 120 ? launch_gemm_f16path<256, 3, 3, 16>(op, args, stream)
+                             : launch_gemm_f16path<128, 4, 4, 16>(op, args, stream);
+    }
+  }
   // <swap, BN, groups per pipeline stage, packed stages, K split, o4, converter warps, epilogue warpgroups>
   if (!skinny) return launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream);
   // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not

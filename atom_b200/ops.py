@@ -16,6 +16,8 @@ __all__ = [
 ]
 
 GEMM_AUTO, GEMM_NO_SPLITK, GEMM_FORCE_TALL, GEMM_FORCE_SKINNY = 0, 1, 2, 4
+GEMM_SPLITK2, GEMM_SPLITK4 = 16, 32
+GEMM_FP16_PATH = 64       # experimental prefill path, see include/atom_b200.h
 
 
 def _stream(t):

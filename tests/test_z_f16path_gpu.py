@@ -1,0 +1,40 @@
+"""GPU suite, OPT-IN (ATOM_EXPERIMENTAL=1): the experimental FP16-path prefill GEMM (ATOM_GEMM_FP16_PATH,
+atom_b200/csrc/gemm_f16path_sm100.cuh).  Written after the round-1 GPU budget was spent and never yet executed on
+hardware, so it is kept out of the default `-m gpu` run; round 2 starts by running it:
+    ATOM_EXPERIMENTAL=1 python -m pytest tests/test_z_f16path_gpu.py -m gpu -q
+Checks: (1) against the numpy model of the kernel's own numerics (oracle.gemm_i4_o16_f16path_model): at most a couple of
+fp16 ulps (the tensor core's FP32 summation order is the only freedom); (2) against the faithful oracle: within 1e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("ATOM_EXPERIMENTAL") != "1",
+                                                  reason="experimental kernel: set ATOM_EXPERIMENTAL=1 to run")]
+
+
+def T(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("m,n,k", [(128, 128, 256), (128, 256, 512), (65, 128, 384), (300, 384, 1024), (256, 1000, 2048),
+                                   (1024, 4096, 4096), (4096, 4096, 4096), (2048, 11008, 4096)])
+def test_f16path_gemm(m, n, k):
+    from atom_b200 import ops
+    t = O.make_gemm_inputs(m, n, k, seed=m + 3 * n + k, pair_shared=True)
+    d = ops.dense_layer_gemm_i4_fp16(*[T(x) for x in t], flags=ops.GEMM_FP16_PATH).cpu().numpy()
+    assert np.isfinite(d.astype(np.float32)).all()
+    rows = None if m * n * k <= (1 << 27) else sorted(set(np.random.default_rng(1).integers(0, m, 16).tolist() + [0, m - 1]))
+    got = (d if rows is None else d[rows]).astype(np.float32)
+    ref = O.gemm_i4_o16(*t, rows=rows).astype(np.float32)
+    assert np.abs(got - ref).max() <= 1.5e-3 * np.abs(ref).max()
+    assert np.abs(got - ref).mean() <= 6e-4 * np.abs(ref).mean()
+    if rows is None:
+        model = O.gemm_i4_o16_f16path_model(*t)
+        ulp = np.abs(d.view(np.int16).astype(np.int32) - model.view(np.int16).astype(np.int32))
+        same_sign = np.signbit(d.astype(np.float32)) == np.signbit(model.astype(np.float32))
+        assert (ulp[same_sign] <= 2).all() and (ulp[same_sign] != 0).mean() < 0.05
