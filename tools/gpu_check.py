@@ -144,6 +144,8 @@ def gtiming(ms_list, n=4096, k=4096):
             variants["skinny"] = 4
         if m > 64:
             variants["tall"] = 2
+            if os.environ.get("ATOM_EXPERIMENTAL") == "1":
+                variants["fp16path"] = 64      # experimental FP16-path prefill kernel (gemm_f16path_sm100.cuh)
         launches = nrot if m <= 512 else 6
         for name, flags in variants.items():
             us = graph_time(lambda i: ops.dense_layer_gemm_i4_fp16(*sets[i % nrot], flags=flags), nrot, launches=launches)
