@@ -11,6 +11,7 @@ Differences (documented in DESIGN.md):
     num_hidden_layers / rms_norm_eps / vocab_size works as `config` (LlamaConfig does).
 """
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -19,6 +20,11 @@ from torch import nn
 from . import ops
 from .cat_tensor import BatchLenInfo
 from .kvcache import BatchedKvCacheInt4
+
+
+# opt-in: prefill-sized fp16-output GEMMs go through the experimental FP16-path kernel (ops.GEMM_FP16_PATH; the library
+# ignores the flag for decode-sized M and for the INT4-output k/v projections)
+_FP16_PATH = os.environ.get("ATOM_B200_FP16_PATH") == "1"
 
 
 @dataclass
@@ -79,6 +85,8 @@ class LinearInt4(nn.Module):
     def forward(self, input, flags=ops.GEMM_AUTO):
         outlier, norms, outlier_scales, norm_scales = input
         f = {"int4": ops.dense_layer_gemm_i4_o4, "fp16": ops.dense_layer_gemm_i4_fp16}[self.out_dtype]
+        if _FP16_PATH and self.out_dtype == "fp16":
+            flags |= ops.GEMM_FP16_PATH
         return f(norms, self.weight_int4, norm_scales, self.scale_int4, outlier, self.weight_int8, outlier_scales, self.scale_int8,
                  flags=flags)
 
