@@ -10,7 +10,7 @@ so that one (page, layer, K-or-V, head) block is `block_len * 64` contiguous byt
 streams with one cp.async.bulk (kv_kernels.cuh).  Differences in mechanism, none in meaning:
   * pages are handed out from a LIFO stack (most recently freed first: still warm in L2), exhaustion raises;
   * the step's page table (CSR indptr / indicies / last_page_offset) is assembled in ONE int32 host buffer and shipped with
-    ONE host->device copy; the three tensors the kernels read are views into it.
+    ONE (blocking) host->device copy; the three tensors the kernels read are views into it.
 """
 from typing import List, Sequence
 
@@ -138,12 +138,11 @@ class BatchedKvCacheInt4:
             n = len(c.indicies)
             table[pos:pos + n] = c.indicies
             pos += n
-        host = torch.from_numpy(table)
-        if pool.device.type == "cuda":
-            host = host.pin_memory()
-        dev = host.to(pool.device, non_blocking=True)
+        # a blocking copy: when the constructor returns the table is valid for every stream (callers hand the object to
+        # side streams and CUDA-graph captures); the steady-state decode loop does not come through here at all
+        # (textgen.DecodeGraphRunner keeps its table in a static buffer)
+        dev = torch.from_numpy(table).to(pool.device)
         self._table = dev                                             # keeps the views alive
-        self._host = host                                             # and the pinned source until the copy has run
         self.data = pool.buf
         self.param = pool.param
         self.indptr = dev[:b + 1]
