@@ -3,7 +3,7 @@
 # ncu is a bench value.  Outputs in gpurun_out/; summarise the .ncu-rep files HERE afterwards with tools/ncu_summary.py
 # and copy the summaries into profiles/.
 #   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/gpu_prof.sh [steps...]'
-# steps (default: all): launches traffic gemm decode quant layer
+# steps (default: launches traffic gemm decode quant layer; extra: f16path)
 set -u
 mkdir -p gpurun_out
 OUT=gpurun_out
@@ -15,13 +15,15 @@ for s in $STEPS; do case $s in
                 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1; grep -c gemm_i4 $OUT/bench_launches.csv ;;
   traffic)  # DRAM bytes per launch of the GEMM at the bench shape and at prefill size -> profiles/ncu_summary.json
             for cfg in "16 0" "16 1" "64 0" "4096 2"; do set -- $cfg
-              timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gemm_i4 -c 6 --csv \
+              timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gemm_ -c 6 --csv \
                   --log-file $OUT/launch_m$1_f$2.csv python tools/prof_gemm.py $1 $2 > /dev/null 2>&1
               echo "== M=$1 flags=$2"; grep -E "gpu__time_duration|dram__bytes" $OUT/launch_m$1_f$2.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}' | tail -6
             done ;;
-  gemm)     timeout 300 ncu $FULL -k regex:gemm_i4 -s 3 -c 1 -f -o $OUT/prof_gemm_m16_split python tools/prof_gemm.py 16 0 > /dev/null 2>&1
-            timeout 300 ncu $FULL -k regex:gemm_i4 -s 3 -c 1 -f -o $OUT/prof_gemm_m16_nosplit python tools/prof_gemm.py 16 1 > /dev/null 2>&1
-            timeout 300 ncu $FULL -k regex:gemm_i4 -s 3 -c 1 -f -o $OUT/prof_gemm_m4096_tall python tools/prof_gemm.py 4096 2 > /dev/null 2>&1 ;;
+  gemm)     timeout 300 ncu $FULL -k regex:gemm_ -s 3 -c 1 -f -o $OUT/prof_gemm_m16_split python tools/prof_gemm.py 16 0 > /dev/null 2>&1
+            timeout 300 ncu $FULL -k regex:gemm_ -s 3 -c 1 -f -o $OUT/prof_gemm_m16_nosplit python tools/prof_gemm.py 16 1 > /dev/null 2>&1
+            timeout 300 ncu $FULL -k regex:gemm_ -s 3 -c 1 -f -o $OUT/prof_gemm_m4096_tall python tools/prof_gemm.py 4096 2 > /dev/null 2>&1 ;;
+  f16path)  # experimental FP16-path prefill kernel (flags 2|64)
+            timeout 300 ncu $FULL -k regex:gemm_ -s 3 -c 1 -f -o $OUT/prof_gemm_m4096_f16path python tools/prof_gemm.py 4096 66 > /dev/null 2>&1 ;;
   decode)   timeout 300 ncu $FULL -k regex:batch_decode -s 2 -c 1 -f -o $OUT/prof_decode python tools/layer_bench.py --copies 1 > /dev/null 2>&1 ;;
   quant)    timeout 300 ncu $FULL -k regex:rmsnorm -s 2 -c 1 -f -o $OUT/prof_rmsnorm python tools/layer_bench.py --copies 1 > /dev/null 2>&1 ;;
   layer)    # per-kernel times of one decode step of a Llama-7B layer
