@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -179,6 +180,23 @@ int launch_gemm_f16path(const GemmOperands& op, const atom::GemmArgs& args, cuda
   return check_launch("gemm_i4 (fp16 path)");
 }
 
+// kBDirect variant: weights already expanded to FP16 (atom_expand_weights_f16); op.b points at W' [N][K] halves.
+template <int BN, int kPack, int kRing, int kConvWarps>
+int launch_gemm_f16path_wx(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
+  using C = atom::F16Cfg<BN, kPack, kRing, kConvWarps, true>;
+  auto kern = atom::gemm_w4a4_f16path_kernel<BN, kPack, kRing, kConvWarps, true>;
+  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (fp16 path, expanded weights)");
+  if (rc) return rc;
+  const uint64_t kp = (uint64_t)(op.K - 128) / 2;
+  CUtensorMap ta4, tbx, ta8;
+  if ((rc = make_map(&ta4, op.a, kp, op.M, kp, 64, C::BM, false))) return rc;
+  if ((rc = make_map(&tbx, op.b, (uint64_t)op.K * 2, op.N, (uint64_t)op.K * 2, 128, BN, true))) return rc;
+  if ((rc = make_map(&ta8, op.ak, 128, op.M, 128, 64, C::BM, false))) return rc;
+  const dim3 grid((unsigned)((op.N + BN - 1) / BN), (unsigned)((op.M + C::BM - 1) / C::BM), 1);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(ta4, tbx, ta8, ta8, args);
+  return check_launch("gemm_i4 (fp16 path, expanded weights)");
+}
+
 template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
@@ -303,6 +321,36 @@ int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, const voi
                     void* d_scale, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream) {
   return gemm_common(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, d, d_scale, M, N, K,
                      flags, stream, true);
+}
+
+int atom_expand_weights_f16(const void* b, const void* b_scale, const void* b_keeper, const void* b_keeper_scale, void* out,
+                            int64_t N, int64_t K, void* stream) {
+  ATOM_REQUIRE(b && b_scale && b_keeper && b_keeper_scale && out, "expand_weights_f16: null pointer argument");
+  ATOM_REQUIRE(N > 0 && N % 8 == 0 && K >= 256 && K % 128 == 0 && N < (1ll << 31) && K < (1ll << 24),
+               "expand_weights_f16: N=%lld must be a positive multiple of 8, K=%lld a multiple of 128 >= 256", (long long)N, (long long)K);
+  ATOM_REQUIRE(aligned16(b) && aligned16(b_keeper) && aligned16(out), "expand_weights_f16: pointers must be 16-byte aligned");
+  const long long total = N * ((K - 128) / 8 + 32);
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  atom::expand_weights_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)b, (const __half*)b_scale, (const int8_t*)b_keeper,
+                                                                           (const __half*)b_keeper_scale, (__half*)out, (int)N, (int)K);
+  return check_launch("expand_weights_f16");
+}
+
+int atom_gemm_i4_o16_wx(const void* a, const void* a_scale, const void* a_keeper, const void* a_keeper_scale, const void* w_expanded,
+                        void* d, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream) {
+  (void)flags;
+  ATOM_REQUIRE(a && a_scale && a_keeper && a_keeper_scale && w_expanded && d, "gemm_i4_o16_wx: null pointer argument");
+  ATOM_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && K >= 256 && K % 128 == 0, "gemm_i4_o16_wx: bad dimensions M=%lld N=%lld K=%lld",
+               (long long)M, (long long)N, (long long)K);
+  ATOM_REQUIRE(aligned16(a) && aligned16(a_keeper) && aligned16(w_expanded) && aligned16(d), "gemm_i4_o16_wx: operand pointers must be 16-byte aligned");
+  ATOM_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 24), "gemm_i4_o16_wx: dimension too large");
+  GemmOperands op{a, w_expanded, a_keeper, nullptr, M, N, K};
+  atom::GemmArgs args{};
+  args.a_scale = (const __half*)a_scale; args.a_keeper_scale = (const __half*)a_keeper_scale;
+  args.d = (__half*)d; args.M = (int)M; args.N = (int)N; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M);
+  const int64_t tiles256 = ((M + 127) / 128) * ((N + 255) / 256);
+  return tiles256 >= 120 ? launch_gemm_f16path_wx<256, 3, 4, 16>(op, args, (cudaStream_t)stream)
+                         : launch_gemm_f16path_wx<128, 4, 5, 16>(op, args, (cudaStream_t)stream);
 }
 
 static int kv_check(const char* what, const void* data, const void* param, const void* indptr, const void* indices,

@@ -40,11 +40,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       : "memory");
 }
 
-template <int BN, int kPack, int kRing, int kConvWarps>
+// kBDirect: the weights were expanded once to FP16 in HBM (expand_weights_f16_kernel below; same element order and 2^8 shift
+// as the in-kernel conversion) and are TMA'd straight into the operand ring -- only the activations are converted.
+template <int BN, int kPack, int kRing, int kConvWarps, bool kBDirect = false>
 struct F16Cfg {
   static constexpr int BM = 128;
   static constexpr int EXP_A = BM * 128, EXP_B = BN * 128;        // one stage: 64 fp16 = 128 B per row
-  static constexpr int PACK_A = BM * 64, PACK_B = BN * 64;        // one packed unit: 64 B per row
+  static constexpr int PACK_A = BM * 64, PACK_B = kBDirect ? 0 : BN * 64;   // one packed unit: 64 B per row
   static constexpr int SCALE_STAGES = 4;                          // scale ring depth, in groups
   static constexpr int SCALE_SLOT = 256 + BN * 2;                 // 64 (lower, upper) A-scale words | BN B-scale halves
   static constexpr int CONV_THREADS = 32 * kConvWarps;
@@ -69,14 +71,15 @@ struct F16Cfg {
   static_assert(THREADS <= 1024, "block size");
 };
 
-template <int BN, int kPack, int kRing, int kConvWarps>
-__global__ void __launch_bounds__(F16Cfg<BN, kPack, kRing, kConvWarps>::THREADS, 1)
+template <int BN, int kPack, int kRing, int kConvWarps, bool kBDirect = false>
+__global__ void __launch_bounds__(F16Cfg<BN, kPack, kRing, kConvWarps, kBDirect>::THREADS, 1)
 gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 activations  (box 64 B x 128 rows)
                          const __grid_constant__ CUtensorMap tm_b4,   // packed INT4 weights      (box 64 B x BN rows)
+                                                                      //   kBDirect: expanded FP16 weights (box 128 B x BN rows, SW128)
                          const __grid_constant__ CUtensorMap tm_a8,   // INT8 keeper, activations (box 64 B x 128 rows, no swizzle)
-                         const __grid_constant__ CUtensorMap tm_b8,   // INT8 keeper, weights     (box 64 B x BN rows, no swizzle)
+                         const __grid_constant__ CUtensorMap tm_b8,   // INT8 keeper, weights     (box 64 B x BN rows, no swizzle; unused if kBDirect)
                          const GemmArgs args) {
-  using C = F16Cfg<BN, kPack, kRing, kConvWarps>;
+  using C = F16Cfg<BN, kPack, kRing, kConvWarps, kBDirect>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -105,10 +108,10 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
     uint8_t* pb = smem + C::OFF_PACK_B + ps * C::PACK_B;
     if (u < G) {
       tma_load_2d(pa, &tm_a4, &pack_full[ps], u * 64, m0);
-      tma_load_2d(pb, &tm_b4, &pack_full[ps], u * 64, n0);
+      if constexpr (!kBDirect) tma_load_2d(pb, &tm_b4, &pack_full[ps], u * 64, n0);
     } else {
       tma_load_2d(pa, &tm_a8, &pack_full[ps], (u - G) * 64, m0);
-      tma_load_2d(pb, &tm_b8, &pack_full[ps], (u - G) * 64, n0);
+      if constexpr (!kBDirect) tma_load_2d(pb, &tm_b8, &pack_full[ps], (u - G) * 64, n0);
     }
   };
   int u_issued = 0;
@@ -117,7 +120,8 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
     for (int i = 0; i < kPack; ++i) mbar_init(&pack_full[i], 1);
     fence_barrier_init();
     for (; u_issued < kPack && u_issued < nunits; ++u_issued) issue_unit(u_issued);
-    tma_prefetch_desc(&tm_a8); tma_prefetch_desc(&tm_b8);
+    tma_prefetch_desc(&tm_a8);
+    if constexpr (!kBDirect) tma_prefetch_desc(&tm_b8);
     for (int i = 0; i < kPack; ++i) mbar_init(&pack_empty[i], kConvWarps);
     for (int i = 0; i < kRing; ++i) { mbar_init(&exp_full[i], kConvWarps); mbar_init(&slot_free[i], 1); }
     for (int i = 0; i < C::SCALE_STAGES; ++i) { mbar_init(&scale_full[i], 32); mbar_init(&scale_empty[i], kConvWarps); }
@@ -169,9 +173,11 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
         const int blk = w >> 3, i = w & 7;
         if (m0 + 16 * blk + i < args.M) cp_async_4(slot + w * 4, as_row + 64 * (m0 / 16 + blk) + 8 * i);
       }
+      if constexpr (!kBDirect) {
 #pragma unroll
-      for (int c = lane; c < BN / 8; c += 32)                  // B-scale: 8 channels per 16-B chunk
-        if (n0 + 8 * c < args.N) cp_async_16(slot + 256 + c * 16, bs_row + n0 + 8 * c);
+        for (int c = lane; c < BN / 8; c += 32)                // B-scale: 8 channels per 16-B chunk
+          if (n0 + 8 * c < args.N) cp_async_16(slot + 256 + c * 16, bs_row + n0 + 8 * c);
+      }
       cp_async_mbar_arrive_noinc(&scale_full[ss]);
     }
   } else if (warp >= 4) {
@@ -188,6 +194,14 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
       const bool first_of_unit = !is_i4 || half_sel == 0, last_of_unit = !is_i4 || half_sel == 1;
       const bool first_of_group = is_i4 ? half_sel == 0 : (u == G), last_of_group = is_i4 ? half_sel == 1 : (u == G + 1);
       if (t >= kRing) mbar_wait(&slot_free[es], ((t / kRing) - 1) & 1);     // the MMAs that read this slot have completed
+      if constexpr (kBDirect) {
+        // stage t of the expanded weights = bytes [128 t, 128 t + 128) of every W' row (both use the converter's K order);
+        // the load counts on exp_full next to the converter warps' arrivals and overlaps the A conversion below
+        if (t_id == 0) {
+          mbar_expect_tx(&exp_full[es], C::EXP_B);
+          tma_load_2d(smem + C::OFF_EXP_B + es * C::EXP_B, &tm_b4, &exp_full[es], t * 128, n0);
+        }
+      }
       if (first_of_unit) mbar_wait(&pack_full[ps], (u / kPack) & 1);
       if (first_of_group) mbar_wait(&scale_full[ss], (sg / C::SCALE_STAGES) & 1);
       const uint8_t* slot = smem + C::OFF_SM + ss * C::SCALE_SLOT;
@@ -219,7 +233,7 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
                            *reinterpret_cast<uint32_t*>(&o[2]), *reinterpret_cast<uint32_t*>(&o[3]));
           }
         }
-        {
+        if constexpr (!kBDirect) {
           uint32_t w[BN / RP];
 #pragma unroll
           for (int k = 0; k < BN / RP; ++k) w[k] = *reinterpret_cast<const uint32_t*>(pb + src_off + k * (RP * 64));
@@ -248,13 +262,15 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
           i8x4_to_f16(w, s2, o);
           *reinterpret_cast<uint2*>(ea + dst_off + k * (RP * 128)) = make_uint2(*reinterpret_cast<uint32_t*>(&o[0]), *reinterpret_cast<uint32_t*>(&o[1]));
         }
+        if constexpr (!kBDirect) {
 #pragma unroll
-        for (int k = 0; k < BN / RP; ++k) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(pb + src_off + k * (RP * 64));
-          const __half2 s2 = __hmul2(__half2half2(sb_halves[r0 + k * RP]), shift_b);
-          __half2 o[2];
-          i8x4_to_f16(w, s2, o);
-          *reinterpret_cast<uint2*>(eb + dst_off + k * (RP * 128)) = make_uint2(*reinterpret_cast<uint32_t*>(&o[0]), *reinterpret_cast<uint32_t*>(&o[1]));
+          for (int k = 0; k < BN / RP; ++k) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(pb + src_off + k * (RP * 64));
+            const __half2 s2 = __hmul2(__half2half2(sb_halves[r0 + k * RP]), shift_b);
+            __half2 o[2];
+            i8x4_to_f16(w, s2, o);
+            *reinterpret_cast<uint2*>(eb + dst_off + k * (RP * 128)) = make_uint2(*reinterpret_cast<uint32_t*>(&o[0]), *reinterpret_cast<uint32_t*>(&o[1]));
+          }
         }
       }
       fence_proxy_async_smem();          // generic-proxy stores -> visible to the tcgen05.mma operand fetch
@@ -301,6 +317,36 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// One-time weight expansion for kBDirect: W'[n][k'] = fp16(w[n][k] * fp16(sB[g][n] * 2^8)) with k' the converter's element
+// order (nib8_to_f16 / i8x4_to_f16 per 32-bit word), row-major [N][K] halves, keeper in the last 128 columns.
+// One thread per 32-bit source word; plain coalesced loads and 16-B / 8-B stores (runs once per weight, HBM-bound).
+__global__ void __launch_bounds__(256)
+expand_weights_f16_kernel(const uint8_t* __restrict__ b, const __half* __restrict__ b_scale, const int8_t* __restrict__ b_keeper,
+                          const __half* __restrict__ b_keeper_scale, __half* __restrict__ out, int N, int K) {
+  const int words4 = (K - 128) / 8, words = words4 + 32;             // INT4 words + keeper words per row
+  const long long total = (long long)N * words;
+  const __half2 shift_b = __float2half2_rn(256.0f);
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(id / words), wi = (int)(id % words);
+    __half* orow = out + (size_t)n * K;
+    if (wi < words4) {
+      const uint32_t w = reinterpret_cast<const uint32_t*>(b + (size_t)n * ((K - 128) / 2))[wi];
+      const __half2 s2 = __hmul2(__half2half2(b_scale[(size_t)(wi >> 4) * N + n]), shift_b);
+      __half2 o[4];
+      nib8_to_f16(w, s2, o);
+      *reinterpret_cast<uint4*>(orow + wi * 8) = make_uint4(*reinterpret_cast<uint32_t*>(&o[0]), *reinterpret_cast<uint32_t*>(&o[1]),
+                                                            *reinterpret_cast<uint32_t*>(&o[2]), *reinterpret_cast<uint32_t*>(&o[3]));
+    } else {
+      const int j = wi - words4;
+      const uint32_t w = reinterpret_cast<const uint32_t*>(b_keeper + (size_t)n * 128)[j];
+      const __half2 s2 = __hmul2(__half2half2(b_keeper_scale[n]), shift_b);
+      __half2 o[2];
+      i8x4_to_f16(w, s2, o);
+      *reinterpret_cast<uint2*>(orow + (K - 128) + j * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&o[0]), *reinterpret_cast<uint32_t*>(&o[1]));
+    }
+  }
 }
 
 }  // namespace atom

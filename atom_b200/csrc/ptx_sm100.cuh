@@ -22,6 +22,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// add `bytes` to the pending transaction count of the current phase without arriving
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~the hint elapses)
 // instead of burning issue slots in a software spin loop.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {

@@ -172,6 +172,20 @@ def gemm_i4_o16_f16path_model(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keep
     return ((af @ bf.T).astype(f32) * f32(1.0 / 256.0)).astype(f16)
 
 
+def expand_weights_f16_model(b, b_scale, b_keeper, b_keeper_scale):
+    """numpy model of atom_expand_weights_f16: f16 [N, K], each 8-element chunk in the converter's order
+    [e0 e4 e1 e5 e2 e6 e3 e7] (keeper columns in natural order), values fp16(w * fp16(scale * 256))."""
+    b, b_keeper = _c(b, np.uint8), _c(b_keeper, np.int8)
+    n, g = b.shape[0], b.shape[1] // 64
+    f32, f16 = np.float32, np.float16
+    sb = (_c(b_scale, np.float16).reshape(-1)[: g * n].reshape(g, n).astype(f32) * 256).astype(f16).astype(f32)
+    sbk = (_c(b_keeper_scale, np.float16)[:n].astype(f32) * 256).astype(f16).astype(f32)
+    w = unpack_int4(b).astype(f32).reshape(n, g, 128) * sb.T[:, :, None]
+    w = w.astype(f16).reshape(n, g * 16, 8)[:, :, [0, 4, 1, 5, 2, 6, 3, 7]].reshape(n, g * 128)
+    wk = (b_keeper.astype(f32) * sbk[:, None]).astype(f16)
+    return np.concatenate([w, wk], 1)
+
+
 # ----------------------------------------------------------------------------------------------
 def pack_int4(q):
     """q: int array [-8,7], last dim even -> uint8 packed low-nibble-first (Reorder.cuh:16-19)."""

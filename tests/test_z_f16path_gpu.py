@@ -38,3 +38,23 @@ def test_f16path_gemm(m, n, k):
         ulp = np.abs(d.view(np.int16).astype(np.int32) - model.view(np.int16).astype(np.int32))
         same_sign = np.signbit(d.astype(np.float32)) == np.signbit(model.astype(np.float32))
         assert (ulp[same_sign] <= 2).all() and (ulp[same_sign] != 0).mean() < 0.05
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("m,n,k", [(128, 128, 256), (300, 384, 1024), (1024, 4096, 4096)])
+def test_f16path_gemm_on_expanded_weights(m, n, k):
+    """kBDirect variant: expand once (bit-exact vs the numpy model), then the GEMM must equal the in-kernel-conversion
+    variant up to FP32 summation order."""
+    from atom_b200 import ops
+    t = O.make_gemm_inputs(m, n, k, seed=m + n + k, pair_shared=True)
+    dev = [T(x) for x in t]
+    wx = ops.expand_weights_f16(dev[1], dev[3], dev[5], dev[7])
+    model = O.expand_weights_f16_model(t[1], t[3], t[5], t[7])
+    assert np.array_equal(wx.cpu().numpy().view(np.uint16), model.view(np.uint16))
+    d_wx = ops.dense_layer_gemm_i4_fp16_wx(dev[0], dev[2], dev[4], dev[6], wx).cpu().numpy()
+    d_in = ops.dense_layer_gemm_i4_fp16(*dev, flags=ops.GEMM_FP16_PATH).cpu().numpy()
+    ulp = np.abs(d_wx.view(np.int16).astype(np.int32) - d_in.view(np.int16).astype(np.int32))
+    assert (ulp <= 2).mean() > 0.999
+    rows = sorted(set(np.random.default_rng(2).integers(0, m, 12).tolist() + [0, m - 1]))
+    ref = O.gemm_i4_o16(*t, rows=rows).astype(np.float32)
+    assert np.abs(d_wx[rows].astype(np.float32) - ref).max() <= 1.5e-3 * np.abs(ref).max()
