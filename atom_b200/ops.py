@@ -32,6 +32,19 @@ def _req_cuda(*ts):
             raise RuntimeError("atom_b200.ops: tensors must be contiguous")
 
 
+def _req_width(what, **named):
+    """Element-width checks (the C ABI takes raw pointers: a float32 tensor where float16 is meant would be silently
+    misread).  Packed INT4 / INT8 operands may be int8 or uint8 views, so only the width is fixed for them."""
+    for spec, t in named.items():
+        name, width = spec.rsplit("_", 1)
+        is_f16 = name.startswith("f16_")
+        name = name[4:] if is_f16 else name
+        ok = isinstance(t, torch.Tensor) and t.element_size() == int(width) and (not is_f16 or t.dtype == torch.float16)
+        if not ok:
+            raise RuntimeError(f"atom_b200.ops.{what}: `{name}` must be a tensor of {width}-byte elements"
+                               f"{' (float16)' if is_f16 else ''}, got {getattr(t, 'dtype', type(t))}")
+
+
 def scale_size(x):
     """ops/__init__.py:137-138"""
     return ((x) // 16 * 64 + 64 - (1 - (x % 16) // 8) * (8 - (x % 8)) * 8)
@@ -48,6 +61,7 @@ def _quant_outputs(bs, hidden_dim, device):
 
 def reorder_fp16_i4(hidden_states, reorder_index):
     """ops/__init__.py:200-219"""
+    _req_width("reorder_fp16_i4", f16_hidden_states_2=hidden_states, reorder_index_2=reorder_index)
     _req_cuda(hidden_states, reorder_index)
     bs, hidden_dim = hidden_states.shape
     out = _quant_outputs(bs, hidden_dim, hidden_states.device)
@@ -61,9 +75,10 @@ def reorder_fp16_i4(hidden_states, reorder_index):
 def rmsnorm_fp16_i4(hidden_states, weight, reorder_index, eps):
     """ops/__init__.py:179-198.  `weight` may be fp32 (LlamaRMSNormInt4 keeps torch.ones fp32, llama.py:237); the
     reference reinterprets its storage as half -- here it is converted, which is what was meant."""
-    _req_cuda(hidden_states, weight, reorder_index)
-    if weight.dtype != torch.float16:
+    if isinstance(weight, torch.Tensor) and weight.dtype != torch.float16:
         weight = weight.to(torch.float16)
+    _req_width("rmsnorm_fp16_i4", f16_hidden_states_2=hidden_states, f16_weight_2=weight, reorder_index_2=reorder_index)
+    _req_cuda(hidden_states, weight, reorder_index)
     bs, hidden_dim = hidden_states.shape
     out = _quant_outputs(bs, hidden_dim, hidden_states.device)
     with torch.cuda.device(hidden_states.device):
@@ -76,6 +91,7 @@ def rmsnorm_fp16_i4(hidden_states, weight, reorder_index, eps):
 
 def activate_fp16_i4(a, b):
     """ops/__init__.py:141-157"""
+    _req_width("activate_fp16_i4", f16_a_2=a, f16_b_2=b)
     _req_cuda(a, b)
     bs, hidden_dim = a.shape
     out = _quant_outputs(bs, hidden_dim, a.device)
@@ -88,6 +104,8 @@ def activate_fp16_i4(a, b):
 
 def dense_layer_gemm_i4_fp16(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, flags=GEMM_AUTO):
     """ops/__init__.py:160-168; dims as punica_ops.cc:236-237 (K = a.size(1)*2 + a_keeper.size(1))."""
+    _req_width("dense_layer_gemm_i4_fp16", a_1=a, b_1=b, f16_a_scale_2=a_scale, f16_b_scale_2=b_scale, a_keeper_1=a_keeper,
+               b_keeper_1=b_keeper, f16_a_keeper_scale_2=a_keeper_scale, f16_b_keeper_scale_2=b_keeper_scale)
     _req_cuda(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale)
     m, n = a.size(0), b.size(0)
     k = a.size(1) * 2 + a_keeper.size(1)
@@ -102,6 +120,8 @@ def dense_layer_gemm_i4_fp16(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keepe
 
 def dense_layer_gemm_i4_o4(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, flags=GEMM_AUTO):
     """ops/__init__.py:171-176"""
+    _req_width("dense_layer_gemm_i4_o4", a_1=a, b_1=b, f16_a_scale_2=a_scale, f16_b_scale_2=b_scale, a_keeper_1=a_keeper,
+               b_keeper_1=b_keeper, f16_a_keeper_scale_2=a_keeper_scale, f16_b_keeper_scale_2=b_keeper_scale)
     _req_cuda(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale)
     m, n = a.size(0), b.size(0)
     k = a.size(1) * 2 + a_keeper.size(1)

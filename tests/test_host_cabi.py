@@ -65,3 +65,24 @@ def test_f16path_operand_conversion_host_check(tmp_path):
     subprocess.check_call(["nvcc", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, os.path.join(root, "tools", "host_check_f16conv.cu")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
+def test_ops_reject_wrong_element_types_before_touching_the_device():
+    """The C ABI takes raw pointers: the Python mirror refuses tensors whose element width cannot be what the kernel reads."""
+    from atom_b200 import ops
+    h16, idx = torch.zeros(2, 256, dtype=torch.float16), torch.arange(256, dtype=torch.int16)
+    with pytest.raises(RuntimeError, match="hidden_states.*2-byte.*float16"):
+        ops.reorder_fp16_i4(h16.float(), idx)
+    with pytest.raises(RuntimeError, match="reorder_index"):
+        ops.reorder_fp16_i4(h16, idx.int())
+    with pytest.raises(RuntimeError, match="`b`"):
+        ops.activate_fp16_i4(h16, h16.float())
+    a, s, kp = torch.zeros(2, 64, dtype=torch.int8), torch.zeros(64, dtype=torch.float16), torch.zeros(2, 128, dtype=torch.int8)
+    with pytest.raises(RuntimeError, match="a_scale"):
+        ops.dense_layer_gemm_i4_fp16(a, a, s.float(), s, kp, kp, s, s)
+    with pytest.raises(RuntimeError, match="CUDA device"):          # widths fine -> the next gate is the device
+        ops.dense_layer_gemm_i4_fp16(a.view(torch.uint8), a, s, s, kp, kp, s, s)
+    with pytest.raises(RuntimeError, match="CUDA device"):          # bfloat16 has the right width but is not float16
+        ops.rmsnorm_fp16_i4(h16, torch.ones(256), idx, 1e-6)        # fp32 norm weight is converted, as for the reference model
+    with pytest.raises(RuntimeError, match="float16"):
+        ops.rmsnorm_fp16_i4(h16.bfloat16(), torch.ones(256), idx, 1e-6)
