@@ -163,10 +163,10 @@ int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
 }
 
 // EXPERIMENTAL FP16-path kernel (gemm_f16path_sm100.cuh): prefill-sized o16 GEMMs only, opt-in through ATOM_GEMM_FP16_PATH.
-template <int BN, int kPack, int kRing, int kConvWarps>
+template <int BN, int kPack, int kRing, int kConvWarps, bool kO4 = false>
 int launch_gemm_f16path(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
   using C = atom::F16Cfg<BN, kPack, kRing, kConvWarps>;
-  auto kern = atom::gemm_w4a4_f16path_kernel<BN, kPack, kRing, kConvWarps>;
+  auto kern = atom::gemm_w4a4_f16path_kernel<BN, kPack, kRing, kConvWarps, false, kO4>;
   int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (fp16 path)");
   if (rc) return rc;
   const uint64_t kp = (uint64_t)(op.K - 128) / 2;
@@ -200,8 +200,10 @@ int launch_gemm_f16path_wx(const GemmOperands& op, const atom::GemmArgs& args, c
 template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
-  if constexpr (!kO4) {
-    if (!skinny && (flags & ATOM_GEMM_FP16_PATH)) {
+  if (!skinny && (flags & ATOM_GEMM_FP16_PATH)) {
+    if constexpr (kO4) {
+      return launch_gemm_f16path<128, 4, 4, 16, true>(op, args, stream);     // one 128-channel head per tile
+    } else {
       // 128 x 256 tiles once they fill the machine (converter work per MMA cycle halves), 128 x 128 below
       const int64_t tiles256 = ((op.M + 127) / 128) * ((op.N + 255) / 256);
       return tiles256 >= 120 ? launch_gemm_f16path<256, 3, 3, 16>(op, args, stream)

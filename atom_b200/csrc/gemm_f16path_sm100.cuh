@@ -71,7 +71,7 @@ struct F16Cfg {
   static_assert(THREADS <= 1024, "block size");
 };
 
-template <int BN, int kPack, int kRing, int kConvWarps, bool kBDirect = false>
+template <int BN, int kPack, int kRing, int kConvWarps, bool kBDirect = false, bool kO4 = false>
 __global__ void __launch_bounds__(F16Cfg<BN, kPack, kRing, kConvWarps, kBDirect>::THREADS, 1)
 gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 activations  (box 64 B x 128 rows)
                          const __grid_constant__ CUtensorMap tm_b4,   // packed INT4 weights      (box 64 B x BN rows)
@@ -80,6 +80,7 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
                          const __grid_constant__ CUtensorMap tm_b8,   // INT8 keeper, weights     (box 64 B x BN rows, no swizzle; unused if kBDirect)
                          const GemmArgs args) {
   using C = F16Cfg<BN, kPack, kRing, kConvWarps, kBDirect>;
+  static_assert(!kO4 || (BN == 128 && C::CPT == 32), "o4: one 128-channel head per tile, 4 column slices of 32");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -289,26 +290,66 @@ gemm_w4a4_f16path_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed 
     const int row = wq * 32 + lane, m = m0 + row;
     const int colbase = (cw >> 2) * C::CPT;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)colbase;
+    if constexpr (!kO4) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < C::CPT; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(taddr + c0, r);
-      tmem_ld_wait();
-      if (m < args.M) {
-        __half* drow = args.d + (size_t)m * args.N + n0 + colbase + c0;
+      for (int c0 = 0; c0 < C::CPT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_wait();
+        if (m < args.M) {
+          __half* drow = args.d + (size_t)m * args.N + n0 + colbase + c0;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          if (n0 + colbase + c0 + i < args.N) {       // N is a multiple of 8 (16-B rows)
-            const __half2 h0 = __floats2half2_rn(__uint_as_float(r[i + 0]) * C::OUT_SCALE, __uint_as_float(r[i + 1]) * C::OUT_SCALE);
-            const __half2 h1 = __floats2half2_rn(__uint_as_float(r[i + 2]) * C::OUT_SCALE, __uint_as_float(r[i + 3]) * C::OUT_SCALE);
-            const __half2 h2 = __floats2half2_rn(__uint_as_float(r[i + 4]) * C::OUT_SCALE, __uint_as_float(r[i + 5]) * C::OUT_SCALE);
-            const __half2 h3 = __floats2half2_rn(__uint_as_float(r[i + 6]) * C::OUT_SCALE, __uint_as_float(r[i + 7]) * C::OUT_SCALE);
-            uint4 v;
-            v.x = *reinterpret_cast<const uint32_t*>(&h0); v.y = *reinterpret_cast<const uint32_t*>(&h1);
-            v.z = *reinterpret_cast<const uint32_t*>(&h2); v.w = *reinterpret_cast<const uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(drow + i) = v;
+          for (int i = 0; i < 32; i += 8) {
+            if (n0 + colbase + c0 + i < args.N) {       // N is a multiple of 8 (16-B rows)
+              const __half2 h0 = __floats2half2_rn(__uint_as_float(r[i + 0]) * C::OUT_SCALE, __uint_as_float(r[i + 1]) * C::OUT_SCALE);
+              const __half2 h1 = __floats2half2_rn(__uint_as_float(r[i + 2]) * C::OUT_SCALE, __uint_as_float(r[i + 3]) * C::OUT_SCALE);
+              const __half2 h2 = __floats2half2_rn(__uint_as_float(r[i + 4]) * C::OUT_SCALE, __uint_as_float(r[i + 5]) * C::OUT_SCALE);
+              const __half2 h3 = __floats2half2_rn(__uint_as_float(r[i + 6]) * C::OUT_SCALE, __uint_as_float(r[i + 7]) * C::OUT_SCALE);
+              uint4 v;
+              v.x = *reinterpret_cast<const uint32_t*>(&h0); v.y = *reinterpret_cast<const uint32_t*>(&h1);
+              v.z = *reinterpret_cast<const uint32_t*>(&h2); v.w = *reinterpret_cast<const uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(drow + i) = v;
+            }
           }
         }
+      }
+    } else {
+      // o4 (DenseLayerGEMM_i4_o4.cu:705-787): per (token, 128-channel head) asymmetric INT4 with the reference's |v| min/max.
+      // The tile is one head; a row's 128 columns sit in 4 warps (same lane quarter, slices of 32): exchange through the
+      // packed ring, which is idle by now (every unit was consumed by these very warps).
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr, r);
+      tmem_ld_wait();
+      float v[32];
+      float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = __uint_as_float(r[i]) * C::OUT_SCALE;
+        const float a = fabsf(v[i]);
+        mx = fmaxf(mx, a); mn = fminf(mn, a);
+      }
+      float* xch = reinterpret_cast<float*>(smem + C::OFF_PACK_A);      // [slice][max | min][128 rows]
+      const int slice = cw >> 2;
+      xch[(slice * 2 + 0) * C::BM + row] = mx;
+      xch[(slice * 2 + 1) * C::BM + row] = mn;
+      asm volatile("bar.sync 1, %0;" ::"n"(C::CONV_THREADS) : "memory");
+#pragma unroll
+      for (int o = 0; o < C::EPI_SLICES; ++o) {
+        mx = fmaxf(mx, xch[(o * 2 + 0) * C::BM + row]);
+        mn = fminf(mn, xch[(o * 2 + 1) * C::BM + row]);
+      }
+      const float scale = (mx - mn) / 15.f, zero = -mn, r_scale = 1.f / scale;
+      if (m < args.M) {
+        if (slice == 0) args.d_scale[(size_t)m * (args.N / 128) + blockIdx.x] = __floats2half2_rn(scale, zero);
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w |= ((uint32_t)((int)roundf((v[i + e] + zero) * r_scale) & 0xF)) << (4 * e);
+          pk[i / 8] = w;
+        }
+        *reinterpret_cast<uint4*>(args.d4 + (size_t)m * (args.N / 2) + (n0 + colbase) / 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
   }

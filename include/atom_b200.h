@@ -42,7 +42,7 @@ extern "C" {
 #define ATOM_GEMM_FORCE_SKINNY 4u /* channels on the MMA-M axis (requires M <= 128 per tile; any M works) */
 #define ATOM_GEMM_SPLITK2 16u     /* decode shapes: force a 2-way K split (default: chosen from the tile count) */
 #define ATOM_GEMM_SPLITK4 32u     /* decode shapes: force a 4-way K split */
-#define ATOM_GEMM_FP16_PATH 64u   /* EXPERIMENTAL, o16 with M > 64 only: scales applied to the operands, FP16 tensor path, one
+#define ATOM_GEMM_FP16_PATH 64u   /* EXPERIMENTAL, M > 64 only (o16 and o4): scales applied to the operands, FP16 tensor path, one
                                      FP32 accumulation over K -- within 1e-3 of the reference, not bit-identical */
 
 ATOM_API int atom_version(void);

@@ -58,3 +58,25 @@ def test_f16path_gemm_on_expanded_weights(m, n, k):
     rows = sorted(set(np.random.default_rng(2).integers(0, m, 12).tolist() + [0, m - 1]))
     ref = O.gemm_i4_o16(*t, rows=rows).astype(np.float32)
     assert np.abs(d_wx[rows].astype(np.float32) - ref).max() <= 1.5e-3 * np.abs(ref).max()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("m,n,k", [(128, 128, 512), (300, 384, 1024), (1024, 4096, 4096)])
+def test_f16path_gemm_o4(m, n, k):
+    """INT4-output epilogue on the FP16 path: (scale, zero) within 1e-3 of the faithful oracle's, dequantised values within
+    one quantisation step (the accumulators differ by operand rounding, so a value next to a rounding boundary may flip)."""
+    from atom_b200 import ops
+    t = O.make_gemm_inputs(m, n, k, seed=m + n + k + 1, pair_shared=True)
+    d, ds = ops.dense_layer_gemm_i4_o4(*[T(x) for x in t], flags=ops.GEMM_FP16_PATH)
+    d, ds = d.cpu().numpy(), ds.cpu().numpy().astype(np.float32).reshape(m, n // 128, 2)
+    rows = sorted(set(np.random.default_rng(3).integers(0, m, 12).tolist() + [0, m - 1]))
+    rd, rds = O.gemm_i4_o4(*t, rows=rows)
+    rds = rds.astype(np.float32).reshape(len(rows), n // 128, 2)
+    assert np.allclose(ds[rows], rds, rtol=2e-3, atol=2e-3 * np.abs(rds).max())
+
+    def deq(q, p):
+        nib = np.stack((q & 0xF, q >> 4), -1).reshape(q.shape[0], n // 128, 128).astype(np.float32)
+        return nib * p[..., :1] - p[..., 1:]
+    step = rds[..., 0].max()
+    assert np.abs(deq(d[rows], ds[rows]) - deq(rd, rds)).max() <= 1.1 * step
+    assert (d[rows] != rd).mean() < 0.05
