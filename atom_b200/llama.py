@@ -22,8 +22,8 @@ from .cat_tensor import BatchLenInfo
 from .kvcache import BatchedKvCacheInt4
 
 
-# opt-in: prefill-sized fp16-output GEMMs go through the experimental FP16-path kernel (ops.GEMM_FP16_PATH; the library
-# ignores the flag for decode-sized M and for the INT4-output k/v projections)
+# opt-in: prefill-sized GEMMs go through the experimental FP16-path kernel (ops.GEMM_FP16_PATH; the library ignores the
+# flag for decode-sized M)
 _FP16_PATH = os.environ.get("ATOM_B200_FP16_PATH") == "1"
 
 
@@ -96,7 +96,7 @@ class LinearInt4(nn.Module):
         if self._w_fp16 is not None and norms.shape[0] > 64:
             return ops.dense_layer_gemm_i4_fp16_wx(norms, norm_scales, outlier, outlier_scales, self._w_fp16)
         f = {"int4": ops.dense_layer_gemm_i4_o4, "fp16": ops.dense_layer_gemm_i4_fp16}[self.out_dtype]
-        if _FP16_PATH and self.out_dtype == "fp16":
+        if _FP16_PATH:
             flags |= ops.GEMM_FP16_PATH
         return f(norms, self.weight_int4, norm_scales, self.scale_int4, outlier, self.weight_int8, outlier_scales, self.scale_int8,
                  flags=flags)
