@@ -24,6 +24,7 @@ _SIGNATURES = {
     "atom_expand_weights_f16": (_I, [_P] * 5 + [_I64, _I64, _P]),
     "atom_gemm_i4_o16_wx": (_I, [_P] * 6 + [_I64, _I64, _I64, _U32, _P]),
     "atom_gemm_set_trace": (_I, [_P]),
+    "atom_set_pdl": (_I, [_I]),
     "atom_batch_decode_i4": (_I, [_P] * 7 + [_I] * 5 + [_P]),
     "atom_append_kv_i4": (_I, [_P] * 9 + [_I] * 5 + [_P]),
     "atom_init_kv_i4": (_I, [_P] * 10 + [_I] * 6 + [_P]),

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -26,6 +27,19 @@ namespace {
 thread_local std::string g_err;
 unsigned long long* g_trace = nullptr;   // atom_gemm_set_trace
 
+// Programmatic dependent launch (opt-in: ATOM_B200_PDL=1 in the environment, or atom_set_pdl): kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and told so (`pdl` argument), so that their prologue -- for the GEMM
+// including the first weight tiles -- overlaps the tail of the preceding kernel.  Off: plain stream order, and the
+// kernels never execute a griddepcontrol instruction.
+int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("ATOM_B200_PDL");
+    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl == 1;
+}
+
 int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -40,6 +54,26 @@ int fail(int code, const char* fmt, ...) {
   do { if (!(cond)) return fail(ATOM_E_INVALID, __VA_ARGS__); } while (0)
 
 int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ATOM_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return ATOM_OK;
+}
+
+// <<<>>> when PDL is off (the validated path, untouched); cudaLaunchKernelEx with the attribute when it is on
+template <typename... KArgs, typename... Args>
+int launch_k(const char* what, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  if (!pdl_enabled()) {
+    kern<<<grid, block, smem, stream>>>(args..., 0);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args..., 1);
+    if (e != cudaSuccess) return fail(ATOM_E_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ATOM_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return ATOM_OK;
@@ -152,12 +186,19 @@ int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = kSplit;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tp4, tq4, tp8, tq8, args);
+  atom::GemmArgs largs = args;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+    largs.pdl = 1;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tp4, tq4, tp8, tq8, largs);
   if (e != cudaSuccess) return fail(ATOM_E_CUDA, "gemm_i4 launch: %s", cudaGetErrorString(e));
   return ATOM_OK;
 }
@@ -272,6 +313,7 @@ const char* atom_last_error(void) { return g_err.c_str(); }
 int atom_scale_index(int row) { return atom::scale_index(row); }
 int atom_scale_size(int rows) { return atom::scale_size(rows); }
 int atom_gemm_set_trace(void* device_buffer) { g_trace = (unsigned long long*)device_buffer; return ATOM_OK; }
+int atom_set_pdl(int enable) { g_pdl = enable ? 1 : 0; return ATOM_OK; }
 
 int atom_reorder_fp16_i4(const void* hidden, const void* reorder_index, int seq_len, int hidden_dim, void* o_outliers,
                          void* o_norms, void* outlier_scales, void* norm_scales, void* stream) {
@@ -279,10 +321,9 @@ int atom_reorder_fp16_i4(const void* hidden, const void* reorder_index, int seq_
   if (rc) return rc;
   ATOM_REQUIRE(hidden && reorder_index && aligned16(hidden), "reorder_fp16_i4: null or misaligned input");
   if ((rc = ensure_dynamic_smem(atom::reorder_quant_kernel, 65536 * 2, "reorder_fp16_i4"))) return rc;   // one fp16 row, hidden <= 65536
-  atom::reorder_quant_kernel<<<seq_len, atom::QUANT_THREADS, (size_t)hidden_dim * 2, (cudaStream_t)stream>>>(
-      (const __half*)hidden, (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms,
-      (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
-  return check_launch("reorder_fp16_i4");
+  return launch_k("reorder_fp16_i4", atom::reorder_quant_kernel, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 2,
+                  (cudaStream_t)stream, (const __half*)hidden, (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers,
+                  (uint8_t*)o_norms, (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
 }
 
 int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, const void* reorder_index, int seq_len,
@@ -293,10 +334,10 @@ int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, cons
   ATOM_REQUIRE(hidden && weight && reorder_index && aligned16(hidden) && aligned16(weight), "rmsnorm_fp16_i4: null or misaligned input");
   ATOM_REQUIRE(hidden_dim <= 32768, "rmsnorm_fp16_i4: hidden_dim=%d > 32768 unsupported", hidden_dim);
   if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel, 32768 * 4 + 512, "rmsnorm_fp16_i4"))) return rc;   // row + weight (fp16) + reduction scratch
-  atom::rmsnorm_quant_kernel<<<seq_len, atom::QUANT_THREADS, (size_t)hidden_dim * 4 + 512, (cudaStream_t)stream>>>(
-      (const __half*)hidden, (const __half*)weight, eps, (const int16_t*)reorder_index, seq_len, hidden_dim,
-      (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
-  return check_launch("rmsnorm_fp16_i4");
+  return launch_k("rmsnorm_fp16_i4", atom::rmsnorm_quant_kernel, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 4 + 512,
+                  (cudaStream_t)stream, (const __half*)hidden, (const __half*)weight, eps, (const int16_t*)reorder_index, seq_len,
+                  hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales, (__half*)norm_scales,
+                  atom::scale_size(seq_len));
 }
 
 int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, int hidden_dim, void* o_outliers, void* o_norms,
@@ -305,10 +346,9 @@ int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, int hidden_
   if (rc) return rc;
   ATOM_REQUIRE(a && b && aligned16(a) && aligned16(b), "activate_fp16_i4: null or misaligned input");
   const long long units = (long long)seq_len * (hidden_dim / 128);
-  atom::activate_quant_kernel<<<(unsigned)((units + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)a, (const __half*)b, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms,
-      (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
-  return check_launch("activate_fp16_i4");
+  return launch_k("activate_fp16_i4", atom::activate_quant_kernel, dim3((unsigned)((units + 7) / 8)), dim3(256), 0, (cudaStream_t)stream,
+                  (const __half*)a, (const __half*)b, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms,
+                  (__half*)outlier_scales, (__half*)norm_scales, atom::scale_size(seq_len));
 }
 
 int atom_gemm_i4_o16(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
@@ -382,10 +422,10 @@ int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, const void
     if ((rc = ensure_dynamic_smem(atom::batch_decode_kernel<8>, 100 * 1024, "batch_decode_i4"))) return rc;
   }
   if (page_size <= 32)
-    atom::batch_decode_kernel<4><<<dim3(batch_size, num_heads), atom::DEC_THREADS, smem, (cudaStream_t)stream>>>((__half*)o, (const __half*)q, kv);
-  else
-    atom::batch_decode_kernel<8><<<dim3(batch_size, num_heads), atom::DEC_THREADS, smem, (cudaStream_t)stream>>>((__half*)o, (const __half*)q, kv);
-  return check_launch("batch_decode_i4");
+    return launch_k("batch_decode_i4", atom::batch_decode_kernel<4>, dim3(batch_size, num_heads), dim3(atom::DEC_THREADS), smem,
+                    (cudaStream_t)stream, (__half*)o, (const __half*)q, kv);
+  return launch_k("batch_decode_i4", atom::batch_decode_kernel<8>, dim3(batch_size, num_heads), dim3(atom::DEC_THREADS), smem,
+                  (cudaStream_t)stream, (__half*)o, (const __half*)q, kv);
 }
 
 int atom_append_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,
@@ -399,9 +439,9 @@ int atom_append_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, cons
   atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
                   (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
   const long long threads = (long long)batch_size * num_heads * 16;
-  atom::append_kv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      kv, (const uint8_t*)k, (const uint8_t*)v, (const __half2*)k_param, (const __half2*)v_param, nullptr, batch_size);
-  return check_launch("append_kv_i4");
+  return launch_k("append_kv_i4", atom::append_kv_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, kv,
+                  (const uint8_t*)k, (const uint8_t*)v, (const __half2*)k_param, (const __half2*)v_param,
+                  (const int32_t*)nullptr, batch_size);
 }
 
 int atom_init_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,
@@ -416,10 +456,9 @@ int atom_init_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const 
   atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
                   (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
   const long long threads = (long long)total_tokens * num_heads * 16;
-  atom::append_kv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      kv, (const uint8_t*)k, (const uint8_t*)v, (const __half2*)k_param, (const __half2*)v_param,
-      (const int32_t*)seqlen_indptr, total_tokens);
-  return check_launch("init_kv_i4");
+  return launch_k("init_kv_i4", atom::append_kv_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, kv,
+                  (const uint8_t*)k, (const uint8_t*)v, (const __half2*)k_param, (const __half2*)v_param,
+                  (const int32_t*)seqlen_indptr, total_tokens);
 }
 
 }  // extern "C"

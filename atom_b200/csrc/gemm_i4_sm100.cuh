@@ -39,6 +39,8 @@ struct GemmArgs {
   int M, N, G;                   // G = number of INT4 groups = K/128 - 1
   int lda_scale;                 // S(M)
   unsigned long long* trace;     // optional device buffer [ctas][128] of clock64 stamps (atom_gemm_set_trace), else null
+  int pdl;                       // launched with programmatic stream serialization: weights may be fetched before the
+                                 // preceding kernel has finished, everything that reads activations waits (griddepcontrol)
 };
 
 // timeline stamps for pipeline debugging (tools/gpu_check.py trace): slot layout per CTA
@@ -177,15 +179,18 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
   // Thread 0 initialises the barriers and immediately fires the first kPack stages of TMA loads: the DRAM round trip
   // of the first tiles (the longest latency on the critical path of a decode-sized problem) then overlaps the TMEM
   // allocation and the CTA-wide sync instead of following them.
-  auto issue_stage = [&](int s, int ps) {
+  // part: 0 = both operands; 1 = arm the barrier and load the WEIGHT tiles only; 2 = load the ACTIVATION tiles only
+  // (PDL: the weights do not depend on the preceding kernel and are fetched before griddepcontrol.wait)
+  auto issue_stage = [&](int s, int ps, int part = 0) {
     const int n4 = stage_int4(s);
-    mbar_arrive_expect_tx(&pack_full[ps], n4 * (C::PACK_P + C::PACK_Q));
+    if (part != 2) mbar_arrive_expect_tx(&pack_full[ps], n4 * (C::PACK_P + C::PACK_Q));
+    const bool do_p = part == 0 || (part == 1) == kSwap, do_q = part == 0 || (part == 1) != kSwap;   // kSwap: P = weights
     for (int j = 0; j < n4; ++j) {
       const int g = g_begin + s * GS + j;
-      tma_load_2d(smem + C::OFF_PACK_P + (ps * GS + j) * C::PACK_P, &tm_p4, &pack_full[ps], g * 64, p0);
-      tma_load_2d(smem + C::OFF_PACK_Q + (ps * GS + j) * C::PACK_Q, &tm_q4, &pack_full[ps], g * 64, q0);
+      if (do_p) tma_load_2d(smem + C::OFF_PACK_P + (ps * GS + j) * C::PACK_P, &tm_p4, &pack_full[ps], g * 64, p0);
+      if (do_q) tma_load_2d(smem + C::OFF_PACK_Q + (ps * GS + j) * C::PACK_Q, &tm_q4, &pack_full[ps], g * 64, q0);
     }
-    if (s < 16) trace_stamp(args, 8 + s);
+    if (s < 16 && part != 1) trace_stamp(args, 8 + s);
   };
   int s_issued = 0;
   if (warp == 0 && lane == 0) {
@@ -193,7 +198,15 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
     // the barriers the first loads need come first; everything else is initialised while those loads are in flight
     for (int i = 0; i < kPack; ++i) mbar_init(&pack_full[i], 1);
     fence_barrier_init();
-    for (; s_issued < kPack && s_issued < nstages && stage_int4(s_issued) > 0; ++s_issued) issue_stage(s_issued, s_issued);
+    if (!args.pdl) {
+      for (; s_issued < kPack && s_issued < nstages && stage_int4(s_issued) > 0; ++s_issued) issue_stage(s_issued, s_issued);
+    } else {
+      griddep_launch_dependents();
+      int s_w = 0;
+      for (; s_w < kPack && s_w < nstages && stage_int4(s_w) > 0; ++s_w) issue_stage(s_w, s_w, 1);
+      griddep_wait();                       // from here on the preceding kernel's output (the activations) may be read
+      for (; s_issued < s_w; ++s_issued) issue_stage(s_issued, s_issued, 2);
+    }
     tma_prefetch_desc(&tm_p8); tma_prefetch_desc(&tm_q8);
     for (int i = 0; i < kPack; ++i) mbar_init(&pack_empty[i], C::CONV_WARPS);
     for (int i = 0; i < C::RING; ++i) {
@@ -247,6 +260,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
     //   [0,256)   MMA-M side: tall  -> 64 (lower,upper) half2 words of the A-scale rows   (word = (r/16)*8 + r%8)
     //                          skinny-> 128 B-scale halves of the channel tile (thread n reads the pair word n/2)
     //   [256,512) MMA-N side: tall  -> BN B-scale halves;  skinny -> BN/16*8 (lower,upper) words of the token rows
+    if (args.pdl) griddep_wait();           // the activation scales are the preceding kernel's output
     for (int s = 0; s < nstages; ++s) {
       const int ss = s % C::SCALE_STAGES;
       if (s >= C::SCALE_STAGES) mbar_wait(&scale_empty[ss], ((s / C::SCALE_STAGES) - 1) & 1);

@@ -30,7 +30,8 @@ __device__ __forceinline__ size_t kv_row(const KvArgs& kv, int page, int which, 
 // append_indptr == nullptr: decode append (one token per sequence, at position seq_len-1).
 __global__ void __launch_bounds__(256)
 append_kv_kernel(KvArgs kv, const uint8_t* __restrict__ k, const uint8_t* __restrict__ v, const __half2* __restrict__ kp,
-                 const __half2* __restrict__ vp, const int32_t* __restrict__ append_indptr, int total_tokens) {
+                 const __half2* __restrict__ vp, const int32_t* __restrict__ append_indptr, int total_tokens, int pdl) {
+  if (pdl) { griddep_launch_dependents(); griddep_wait(); }
   const long long unit = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;   // (token, head)
   const int sub = threadIdx.x & 15;
   if (unit >= (long long)total_tokens * kv.H) return;
@@ -87,8 +88,9 @@ __device__ __forceinline__ __half2 nib2(uint32_t w, int q) {
 
 template <int kMaxTpl>   // tokens per lane per page = P / 8 <= kMaxTpl
 __global__ void __launch_bounds__(DEC_THREADS, 4)
-batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs kv) {
+batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs kv, int pdl) {
   extern __shared__ __align__(128) uint8_t smem_d[];
+  if (pdl) { griddep_launch_dependents(); griddep_wait(); }      // q and the newest KV entry come from the preceding kernels
   const int P = kv.P;
   const int stage_bytes = 2 * 64 * P + 2 * 4 * P;                   // K | V | K params | V params
   uint8_t* ring = smem_d;

@@ -167,6 +167,13 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) {
   float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream (if it was launched with the programmatic-serialization attribute) may
+// start its prologue once every CTA of this grid has executed this (or exited).  wait: blocks until the preceding grid has
+// completed and its memory operations are visible; without a programmatic dependency both are no-ops.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   uint4 v;

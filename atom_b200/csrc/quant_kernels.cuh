@@ -53,8 +53,9 @@ constexpr int QUANT_THREADS = 512, QUANT_WARPS = QUANT_THREADS / 32;
 __global__ void __launch_bounds__(QUANT_THREADS)
 reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ idx, int seq_len, int hidden,
                      int8_t* __restrict__ s8out, uint8_t* __restrict__ s4out, __half* __restrict__ s8scale,
-                     __half* __restrict__ s4scale, int scale_ldm) {
+                     __half* __restrict__ s4scale, int scale_ldm, int pdl) {
   extern __shared__ __align__(16) uint8_t smem_q[];
+  if (pdl) { griddep_launch_dependents(); griddep_wait(); }      // opt-in PDL: the input is the preceding kernel's output
   __half* xs = reinterpret_cast<__half*>(smem_q);
   const int row = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ng = hidden / 128;
@@ -80,8 +81,9 @@ reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ i
 __global__ void __launch_bounds__(QUANT_THREADS)
 rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w, float eps, const int16_t* __restrict__ idx,
                      int seq_len, int hidden, int8_t* __restrict__ s8out, uint8_t* __restrict__ s4out,
-                     __half* __restrict__ s8scale, __half* __restrict__ s4scale, int scale_ldm) {
+                     __half* __restrict__ s8scale, __half* __restrict__ s4scale, int scale_ldm, int pdl) {
   extern __shared__ __align__(16) uint8_t smem_q[];
+  if (pdl) { griddep_launch_dependents(); griddep_wait(); }
   __half* xs = reinterpret_cast<__half*>(smem_q);
   __half* ws = xs + hidden;                             // norm weight staged too: the gather then never touches global
   float* red = reinterpret_cast<float*>(smem_q + (size_t)hidden * 4);
@@ -149,7 +151,8 @@ __device__ __forceinline__ float silu_ref(float x) { return x / (1.0f + expf(-x)
 __global__ void __launch_bounds__(256)
 activate_quant_kernel(const __half* __restrict__ a, const __half* __restrict__ b, int seq_len, int hidden,
                       int8_t* __restrict__ s8out, uint8_t* __restrict__ s4out, __half* __restrict__ s8scale,
-                      __half* __restrict__ s4scale, int scale_ldm) {
+                      __half* __restrict__ s4scale, int scale_ldm, int pdl) {
+  if (pdl) { griddep_launch_dependents(); griddep_wait(); }
   const int ng = hidden / 128;
   const long long unit = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (unit >= (long long)seq_len * ng) return;

@@ -96,6 +96,12 @@ ATOM_API int atom_gemm_i4_o16_wx(const void* a, const void* a_scale, const void*
  * stages to device_buffer[cta*128 ...] (layout in gemm_i4_sm100.cuh).  NULL switches tracing off. */
 ATOM_API int atom_gemm_set_trace(void* device_buffer);
 
+/* EXPERIMENTAL (no reference counterpart; not yet run on hardware): programmatic dependent launch.  When enabled (also via
+ * ATOM_B200_PDL=1 in the environment) every kernel is launched with programmatic stream serialization: its prologue -- for
+ * the GEMM including the first weight tiles -- overlaps the tail of the preceding kernel; everything that reads that
+ * kernel's output waits on griddepcontrol.wait.  Results are unchanged.  Off by default. */
+ATOM_API int atom_set_pdl(int enable);
+
 /* replaces batch_decode_i4 (punica_ops.cc:82-120 -> FlashInferBatchDecodeKernel_i4<128>, flashinfer_impl.cuh:9-46)
  *   o,q f16 [B,H,128]  kv_data u8 [pages,L,2,H,P,64]  kv_param f16 [pages,L,2,H,P,2]
  *   kv_indptr i32 [B+1]  kv_indices i32 [nnz]  last_page_offset i32 [B] */
