@@ -150,6 +150,12 @@ def gtiming(ms_list, n=4096, k=4096):
         for name, flags in variants.items():
             us = graph_time(lambda i: ops.dense_layer_gemm_i4_fp16(*sets[i % nrot], flags=flags), nrot, launches=launches)
             rec[name] = {"us": round(us, 2), "TOPS": round(ops_count / us * 1e-6, 1)}
+        if "fp16path" in variants:       # same kernel fed from weights expanded to FP16 once (prefill cache variant)
+            wx = [ops.expand_weights_f16(s_[1], s_[3], s_[5], s_[7]) for s_ in sets]
+            us = graph_time(lambda i: ops.dense_layer_gemm_i4_fp16_wx(sets[i % nrot][0], sets[i % nrot][2], sets[i % nrot][4],
+                                                                      sets[i % nrot][6], wx[i % nrot]), nrot, launches=launches)
+            rec["fp16path_wx"] = {"us": round(us, 2), "TOPS": round(ops_count / us * 1e-6, 1)}
+            del wx
         if R.available() and m in (16, 4096):
             us = graph_time(lambda i: R.gemm_i4_o16(*sets[i % nrot], d=outs[i % nrot], sync=0), nrot, launches=4, reps=5) \
                 if False else None   # the reference launches on the legacy stream: not capturable; use event timing
