@@ -261,7 +261,9 @@ int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t f
   // wave of CTAs costs a full pipeline ramp (first TMA tile ~2 us after launch).
   const int64_t tiles = ch_tiles * ((op.M + 63) / 64);
   int ksplit = 1;
-  if (!(flags & ATOM_GEMM_NO_SPLITK) && groups >= 8) {
+  // o4 quantises from the FP32 sums: a K split would reorder them and move INT4 codes by one, so the KV projections
+  // never split (bit-identical codes to the reference kernel on every path)
+  if (!kO4 && !(flags & ATOM_GEMM_NO_SPLITK) && groups >= 8) {
     if (flags & ATOM_GEMM_SPLITK2) ksplit = 2;
     else if (flags & ATOM_GEMM_SPLITK4) ksplit = 4;
     else ksplit = tiles * 4 <= 148 ? 4 : (tiles * 2 <= 148 ? 2 : 1);   // the largest split that still fits one wave of 148 SMs
@@ -287,6 +289,9 @@ int gemm_common(const void* a, const void* b, const void* a_scale, const void* b
   ATOM_REQUIRE(!o4 || (N % 128 == 0 && d_scale), "gemm_i4_o4: N=%lld must be a multiple of 128 (one head per scale)", (long long)N);
   ATOM_REQUIRE(aligned16(a) && aligned16(b) && aligned16(a_keeper) && aligned16(b_keeper) && aligned16(d),
                "gemm_i4: operand pointers must be 16-byte aligned");
+  ATOM_REQUIRE(aligned16(b_scale) && aligned16(b_keeper_scale), "gemm_i4: weight scale pointers must be 16-byte aligned");
+  ATOM_REQUIRE((reinterpret_cast<uintptr_t>(a_scale) & 3) == 0 && (reinterpret_cast<uintptr_t>(a_keeper_scale) & 3) == 0,
+               "gemm_i4: activation scale pointers must be 4-byte aligned");
   ATOM_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 24), "gemm_i4: dimension too large");
   GemmOperands op{a, b, a_keeper, b_keeper, M, N, K};
   atom::GemmArgs args{};

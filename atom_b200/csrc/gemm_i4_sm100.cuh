@@ -219,6 +219,9 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // split-K: a CTA's shared memory may only be written remotely once that CTA has started -- every thread arrives
+  // here (cheap, non-blocking) and the epilogue warps wait right before their first st.shared::cluster
+  if constexpr (kSplit > 1) cluster_arrive_relaxed();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) trace_stamp(args, 1);
 
@@ -288,6 +291,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
   } else if ((warp >= 4 && warp < 8) || warp >= 8 + 4 * C::EPI_WGS) {
     // ============================================================ converter warps
     const int t = (warp < 8 ? warp - 4 : warp - 8 - 4 * C::EPI_WGS + 4) * 32 + lane;
+    if (args.pdl && t == 0) griddep_wait();   // thread 0 TMA-loads the activation keeper: the preceding kernel's output
     for (int s = 0; s < nstages; ++s) {
       const int es = s % C::RING, ps = s % kPack;
       const int ng = stage_groups(s), n4 = stage_int4(s);
@@ -412,6 +416,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
     // Remote stores need no round trip (a pull would put several DSMEM read latencies on the critical path); one
     // cluster barrier (release / acquire) publishes them, then only the leader goes on.
     if constexpr (kSplit > 1) {
+      cluster_wait();                 // pairs with the setup arrive: every CTA of the cluster is running
       if (krank != 0) {
         const uint32_t remote = mapa_shared(smem_u32(smem + C::OFF_RED), 0) + (krank - 1) * C::RED_BYTES;
 #pragma unroll
@@ -534,7 +539,7 @@ gemm_i4_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4, MMA-
 
   // ---------------------------------------------------------------- teardown
   if constexpr (kSplit > 1) {
-    if (!(warp >= 8 && warp < 8 + 4 * C::EPI_WGS)) { cluster_arrive(); cluster_wait(); }   // pairs with the epilogue's barrier
+    if (!(warp >= 8 && warp < 8 + 4 * C::EPI_WGS)) { cluster_wait(); cluster_arrive(); cluster_wait(); }   // setup phase, then the epilogue's publish phase
   }
   tc_fence_before();
   __syncthreads();

@@ -39,6 +39,7 @@ class QLinearLayer(nn.Module):
             self.bias = None
         self.packed = False
         self._w_unquantized = None
+        self._quantized = False
 
     @torch.no_grad()
     def forward(self, x):
@@ -66,7 +67,10 @@ class QLinearLayer(nn.Module):
             return
         if getattr(a, "keeper_precision", 0) not in (0, 3):
             raise NotImplementedError("FP8 keepers are outside the W4A4 INT path")
-        self._w_unquantized = self.weight.clone()
+        # The FP weight is only needed again by int4_operands() / pack() / to_int4(); keeping it doubles the simulator's
+        # weight memory (+130 GB for Llama-65B), so it is opt-in: args.keep_fp_for_export, freed again by pack().
+        self._w_unquantized = self.weight.clone() if getattr(a, "keep_fp_for_export", False) else None
+        self._quantized = True
         if a.keeper > 0:
             saved = self.weight[:, -a.keeper:].clone().contiguous()
             if a.keeper_precision == 3:
@@ -93,6 +97,9 @@ class QLinearLayer(nn.Module):
         changing the layer.  Requires the W4A4 recipe: wbits=4, symmetric, weight_group_size=128, keeper=128 (INT8)."""
         a = self.args
         assert a.wbits == 4 and a.w_sym and a.weight_group_size == 128 and a.keeper == 128 and a.weight_channel_group == 2, "pack() implements the W4A4/g128/keeper128 recipe"
+        if getattr(self, "_quantized", False) and self._w_unquantized is None:
+            raise RuntimeError("QLinearLayer was fake-quantised without args.keep_fp_for_export=True: the FP weight needed to "
+                               "derive real INT4 operands is gone (call pack()/to_int4() before quant(), or set the flag)")
         w = (self._w_unquantized if self._w_unquantized is not None else self.weight).float().cpu()
         out_f, in_f = w.shape
         assert in_f % 128 == 0 and in_f >= 256 and out_f % 8 == 0
@@ -123,4 +130,5 @@ class QLinearLayer(nn.Module):
             self.register_buffer(k, v.to(dev))
         self.register_buffer("identity_index", torch.arange(self.weight.shape[1], dtype=torch.int16, device=dev))
         self.packed = True
+        self._w_unquantized = None          # the saved FP copy has served its purpose
         return self

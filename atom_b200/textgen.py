@@ -278,6 +278,15 @@ class DecodeGraphRunner:
         return e["out"].cpu().numpy()               # synchronises: the caller needs the tokens to go on
 
 
+def _vocab_size(model) -> int:
+    """Prompt ids must index the model's own embedding table (the reference hard-codes 32000, bench_textgen.py:119)."""
+    head = getattr(model, "lm_head", None)
+    if head is not None and hasattr(head, "out_features"):
+        return int(head.out_features)
+    cfg = getattr(model, "config", None) or getattr(getattr(model, "model", None), "config", None)
+    return int(getattr(cfg, "vocab_size", 32000))
+
+
 def pool_capacity(batch_size: int, maxlen: int, block_len: int) -> int:
     """Pages for `batch_size` sequences of up to `maxlen` tokens (+1 spare page each), bench_textgen.py:99."""
     return batch_size * ((maxlen + block_len - 1) // block_len + 1)
@@ -289,7 +298,7 @@ def run_textgen(model: Callable, rs: RequestSet, cfg: TextGenConfig, pool: KvPoo
     """Drive `model(input_ids, blen, prefill_kv, decode_kv) -> (logits, hidden)` through the whole request set.
     Latencies are wall-clock around the step *including* the device->host read of the next tokens (which synchronises),
     as in the reference.  With a `decode_runner`, steps that admit no new request are replayed from its CUDA graphs."""
-    sched = TextGenScheduler(rs, cfg.batch_size, pool, device)
+    sched = TextGenScheduler(rs, cfg.batch_size, pool, device, vocab_size=_vocab_size(model))
     steps = graphed = 0
     t_start = time.perf_counter()
     while not sched.finished:

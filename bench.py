@@ -154,7 +154,10 @@ def main():
     sets = [one] + [tuple(t.clone() for t in one) for _ in range(R_sets - 1)]
     outs = [torch.empty((M, N), dtype=torch.float16, device=dev) for _ in range(R_sets)]
     op_count = 2.0 * M * N * K
-    stream = torch.cuda.Stream(dev)
+    # The reference launcher uses the LEGACY default stream (GEMM.cuh:763): its arm is enqueued, timed and synchronised on
+    # exactly that stream (torch's default stream is the legacy stream), so the events bracket the kernels.  A non-blocking
+    # side stream would not order against legacy-stream work at all and the events would time the CPU enqueue rate.
+    stream = torch.cuda.default_stream(dev) if ref_mode else torch.cuda.Stream(dev)
 
     def run_batch():
         if ref_mode:   # the reference launches on the legacy default stream (GEMM.cuh:763): not capturable, plain loop
@@ -191,19 +194,24 @@ def main():
     with torch.cuda.stream(stream):
         t_w = time.perf_counter()
         n_w = 0
-        while n_w < max(a.warmup, 3) or (time.perf_counter() - t_w < 0.4 and not ref_mode):
+        while n_w < max(a.warmup, 3) or time.perf_counter() - t_w < 0.4:     # same warm-up rule for both arms
             step(); n_w += 1
             if n_w % 50 == 0:
                 stream.synchronize()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        w0 = time.perf_counter()
         e0.record(stream)
         for _ in range(a.steps):
             step()
         e1.record(stream)
         barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3
         ms = e0.elapsed_time(e1)
+        # the events sit on the stream the kernels run on, so the device time they bracket must account for (nearly) all
+        # of the host's wall clock between the two synchronising barriers; a large gap means they did not bracket the work
+        assert ms >= 0.7 * wall_ms - 1.0, f"timing contract broken: events {ms:.3f} ms vs wall clock {wall_ms:.3f} ms"
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -273,6 +281,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_tops = op_count * e2e_steps * world / t.item() * 1e-12
+    # self-check of the timing contract: one device-timed launch cannot take longer than a whole synchronised e2e step
+    # (H2D + the same launch + D2H + sync); if it does, the events did not bracket the kernels
+    e2e_us_per_step = t.item() / e2e_steps * 1e6
+    assert ms_per_step * 1e3 / R_sets <= e2e_us_per_step * 1.05, \
+        f"timing contract broken: {ms_per_step * 1e3 / R_sets:.2f} us per launch (events) > {e2e_us_per_step:.2f} us per e2e step"
 
     if rank != 0:
         if world > 1:

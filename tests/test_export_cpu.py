@@ -21,7 +21,7 @@ from oracle import oracle as O
 
 
 def _args():
-    return types.SimpleNamespace(wbits=4, abits=4, w_sym=True, a_sym=True, weight_group_size=128, act_group_size=128,
+    return types.SimpleNamespace(keep_fp_for_export=True, wbits=4, abits=4, w_sym=True, a_sym=True, weight_group_size=128, act_group_size=128,
                                  weight_channel_group=2, w_clip_ratio=0.85, a_clip_ratio=1.0, keeper=128, keeper_precision=3,
                                  exponential=False, tiling=0, quant_type="int", static=False, kv_clip_ratio=1.0, reorder=True,
                                  kv_cache=True)

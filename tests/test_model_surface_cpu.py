@@ -40,7 +40,11 @@ def test_qlinear_quant_matches_reference_and_pack_dequantises_to_it(gold):
     from oracle import oracle as O
     lin = torch.nn.Linear(512, 256, bias=False)
     lin.weight.data = torch.from_numpy(gold["w0"]).clone()
-    q = QLinearLayer(lin, _args())
+    plain = QLinearLayer(torch.nn.Linear(512, 256, bias=False), _args())
+    plain.quant()
+    with pytest.raises(RuntimeError, match="keep_fp_for_export"):                    # the FP weight is not kept by default
+        plain.pack(device="cpu")
+    q = QLinearLayer(lin, _args(keep_fp_for_export=True))
     q.quant()
     assert torch.equal(q.weight, torch.from_numpy(gold["wq"]))                       # fake-quant weight: bit exact
     y = q(Q.quantize_activation_wrapper(torch.from_numpy(gold["x"]).clone(), _args()))
@@ -160,9 +164,11 @@ def test_mixtral_drivers_reorder_is_function_preserving_and_router_stays_fp():
     q = layers[0]
     assert torch.allclose(q(x)[0], y_fp, atol=1e-4)              # a permutation applied consistently changes nothing
     gate_w = q.block_sparse_moe.gate.weight.clone()
+    w1_fp = q.block_sparse_moe.experts[0].w1.weight.clone()
     modelutils.quantize_model_mixtral(layers, a)
     assert torch.equal(q.block_sparse_moe.gate.weight, gate_w)    # router untouched (modelutils_mixtral.py:139-145)
-    assert not torch.equal(q.block_sparse_moe.experts[0].w1.weight, q.block_sparse_moe.experts[0].w1._w_unquantized)
+    assert not torch.equal(q.block_sparse_moe.experts[0].w1.weight, w1_fp)
+    assert q.block_sparse_moe.experts[0].w1._w_unquantized is None     # no FP copy unless args.keep_fp_for_export
     modelutils.add_act_quant_wrapper_mixtral(layers, a)
     y4, router = q(x, output_router_logits=True)
     assert torch.isfinite(y4).all() and router.shape == (6, 4)

@@ -105,3 +105,21 @@ def test_decode_graph_runner_static_buffers_equal_the_eager_page_tables():
         pool = KvPoolInt4(1, 2, 128, 64, block, torch.device("cpu"))
         tg.run_textgen(_FakeLM(97, bs, block), rs, tg.TextGenConfig(bs), pool, torch.device("cpu"),
                        decode_runner=tg.DecodeGraphRunner(_FakeLM(97, bs, block), pool, "cpu", max_pages_per_seq=1, capture=False))
+
+
+def test_prompt_ids_follow_the_models_vocabulary():
+    """round-1 GPU failure: prompts were drawn from the default 32000-entry vocabulary for a 128-entry embedding table."""
+    class _Head:
+        out_features = 23
+
+    class _SmallVocabLM(_FakeLM):
+        lm_head = _Head()
+
+        def __call__(self, ids, blen, prefill_kv, decode_kv):
+            assert int(ids.max()) < 23, "prompt id outside the model's embedding table"
+            return super().__call__(ids, blen, prefill_kv, decode_kv)
+
+    rs = tg.generate_request_set(5, 64)
+    pool = KvPoolInt4(1, 2, 128, tg.pool_capacity(2, 64, 16), 16, torch.device("cpu"))
+    res = tg.run_textgen(_SmallVocabLM(23, 2, 16), rs, tg.TextGenConfig(2), pool, torch.device("cpu"), keep_tokens=True)
+    assert all(0 <= t < 23 for toks in res.tokens for t in toks)
