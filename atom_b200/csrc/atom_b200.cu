@@ -18,7 +18,7 @@
 
 #include "../../include/atom_b200.h"
 #include "gemm_i4_sm100.cuh"
-#include "gemm_f16path_sm100.cuh"
+#include "gemm_i4_skinny_sm100.cuh"
 #include "kv_kernels.cuh"
 #include "quant_kernels.cuh"
 
@@ -133,9 +133,10 @@ std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // 2-D byte tensor [rows][inner] with row pitch `pitch`; box = box_rows x box_inner bytes; OOB rows read as zero.
+// swizzle: 0 = none, 1 = SWIZZLE_128B, 2 = SWIZZLE_64B
 int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch, uint32_t box_inner,
-             uint32_t box_rows, bool swizzle128) {
-  MapKey key{ptr, inner, rows, pitch, box_inner, box_rows, swizzle128 ? 1u : 0u};
+             uint32_t box_rows, int swizzle) {
+  MapKey key{ptr, inner, rows, pitch, box_inner, box_rows, (uint32_t)swizzle};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -148,7 +149,8 @@ int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, u
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ATOM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   std::lock_guard<std::mutex> lk(g_map_mu);
@@ -175,10 +177,10 @@ int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
   const void* p8 = kSwap ? op.bk : op.ak; const void* q8 = kSwap ? op.ak : op.bk;
   const uint64_t prow = kSwap ? op.N : op.M, qrow = kSwap ? op.M : op.N;
   CUtensorMap tp4, tq4, tp8, tq8;
-  if ((rc = make_map(&tp4, p4, kp, prow, kp, 64, C::BM, false))) return rc;
-  if ((rc = make_map(&tq4, q4, kp, qrow, kp, 64, BN, false))) return rc;
-  if ((rc = make_map(&tp8, p8, 128, prow, 128, 128, C::BM, true))) return rc;
-  if ((rc = make_map(&tq8, q8, 128, qrow, 128, 128, BN, true))) return rc;
+  if ((rc = make_map(&tp4, p4, kp, prow, kp, 64, C::BM, 0))) return rc;
+  if ((rc = make_map(&tq4, q4, kp, qrow, kp, 64, BN, 0))) return rc;
+  if ((rc = make_map(&tp8, p8, 128, prow, 128, 128, C::BM, 1))) return rc;
+  if ((rc = make_map(&tq8, q8, 128, qrow, 128, 128, BN, 1))) return rc;
 
   const int ch_tile = kSwap ? C::BM : BN, tok_tile = kSwap ? BN : C::BM;
   cudaLaunchConfig_t cfg{};
@@ -203,56 +205,86 @@ int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
   return ATOM_OK;
 }
 
-// EXPERIMENTAL FP16-path kernel (gemm_f16path_sm100.cuh): prefill-sized o16 GEMMs only, opt-in through ATOM_GEMM_FP16_PATH.
-template <int BN, int kPack, int kRing, int kConvWarps, bool kO4 = false>
-int launch_gemm_f16path(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
-  using C = atom::F16Cfg<BN, kPack, kRing, kConvWarps>;
-  auto kern = atom::gemm_w4a4_f16path_kernel<BN, kPack, kRing, kConvWarps, false, kO4>;
-  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (fp16 path)");
-  if (rc) return rc;
-  const uint64_t kp = (uint64_t)(op.K - 128) / 2;
-  CUtensorMap ta4, tb4, ta8, tb8;
-  if ((rc = make_map(&ta4, op.a, kp, op.M, kp, 64, C::BM, false))) return rc;
-  if ((rc = make_map(&tb4, op.b, kp, op.N, kp, 64, BN, false))) return rc;
-  if ((rc = make_map(&ta8, op.ak, 128, op.M, 128, 64, C::BM, false))) return rc;
-  if ((rc = make_map(&tb8, op.bk, 128, op.N, 128, 64, BN, false))) return rc;
-  const dim3 grid((unsigned)((op.N + BN - 1) / BN), (unsigned)((op.M + C::BM - 1) / C::BM), 1);
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(ta4, tb4, ta8, tb8, args);
-  return check_launch("gemm_i4 (fp16 path)");
+// Decode-shape kernel (gemm_i4_skinny_sm100.cuh): weights expanded into tensor memory, two CTAs per SM, always launched
+// with programmatic stream serialization (the kernel fetches only weights before griddepcontrol.wait).
+int g_gemm_pdl = -1;
+bool gemm_pdl_enabled() {
+  if (g_gemm_pdl < 0) {
+    const char* e = getenv("ATOM_B200_GEMM_PDL");
+    g_gemm_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_gemm_pdl == 1;
 }
 
-// kBDirect variant: weights already expanded to FP16 (atom_expand_weights_f16); op.b points at W' [N][K] halves.
-template <int BN, int kPack, int kRing, int kConvWarps>
-int launch_gemm_f16path_wx(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
-  using C = atom::F16Cfg<BN, kPack, kRing, kConvWarps, true>;
-  auto kern = atom::gemm_w4a4_f16path_kernel<BN, kPack, kRing, kConvWarps, true>;
-  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (fp16 path, expanded weights)");
+template <int BN, int kSplit, int kEpi>
+int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
+  using C = atom::SkinnyCfg<BN, kSplit, kEpi>;
+  auto kern = atom::gemm_i4_skinny_kernel<BN, kSplit, kEpi>;
+  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (skinny)");
   if (rc) return rc;
   const uint64_t kp = (uint64_t)(op.K - 128) / 2;
-  CUtensorMap ta4, tbx, ta8;
-  if ((rc = make_map(&ta4, op.a, kp, op.M, kp, 64, C::BM, false))) return rc;
-  if ((rc = make_map(&tbx, op.b, (uint64_t)op.K * 2, op.N, (uint64_t)op.K * 2, 128, BN, true))) return rc;
-  if ((rc = make_map(&ta8, op.ak, 128, op.M, 128, 64, C::BM, false))) return rc;
-  const dim3 grid((unsigned)((op.N + BN - 1) / BN), (unsigned)((op.M + C::BM - 1) / C::BM), 1);
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(ta4, tbx, ta8, ta8, args);
-  return check_launch("gemm_i4 (fp16 path, expanded weights)");
+  CUtensorMap tp4, tq4, tp8, tq8;
+  if ((rc = make_map(&tp4, op.b, kp, op.N, kp, 64, C::BM, 2))) return rc;
+  if ((rc = make_map(&tq4, op.a, kp, op.M, kp, 64, BN, 0))) return rc;
+  if ((rc = make_map(&tp8, op.bk, 128, op.N, 128, 128, C::BM, 1))) return rc;
+  if ((rc = make_map(&tq8, op.ak, 128, op.M, 128, 128, BN, 1))) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((op.N + C::BM - 1) / C::BM), (unsigned)((op.M + BN - 1) / BN), kSplit);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = kSplit;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (gemm_pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tp4, tq4, tp8, tq8, args);
+  if (e != cudaSuccess) return fail(ATOM_E_CUDA, "gemm_i4 (skinny) launch: %s", cudaGetErrorString(e));
+  return ATOM_OK;
+}
+
+template <bool kO4>
+int skinny_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
+  constexpr int kEpi = kO4 ? atom::EPI_O4 : atom::EPI_O16;
+  const int64_t ch_tiles = (op.N + 127) / 128;
+  const int groups = args.G + 1;
+  const int bn = op.M <= 16 ? 16 : (op.M <= 32 ? 32 : 64);
+  const int64_t tiles = ch_tiles * ((op.M + bn - 1) / bn);
+  // K split over a cluster (1, 2 or 4 ranks) until the CTAs cover the machine: 148 SMs, two CTAs resident on each for
+  // the 16- and 32-token tiles.  Every rank must keep at least ~4 groups, or the fixed cost per CTA dominates.
+  int ksplit = 1;
+  if (!kO4 && !(flags & ATOM_GEMM_NO_SPLITK)) {
+    if (flags & ATOM_GEMM_SPLITK2) ksplit = 2;
+    else if (flags & ATOM_GEMM_SPLITK4) ksplit = 4;
+    else if (groups >= 8) ksplit = tiles * 4 <= 160 ? 4 : (tiles * 2 <= 160 ? 2 : 1);
+  }
+  if constexpr (kO4) {
+    if (bn == 16) return launch_skinny<16, 1, kEpi>(op, args, stream);
+    if (bn == 32) return launch_skinny<32, 1, kEpi>(op, args, stream);
+    return launch_skinny<64, 1, kEpi>(op, args, stream);
+  } else {
+#define ATOM_SK(BN_)                                                                 \
+  return ksplit == 4   ? launch_skinny<BN_, 4, kEpi>(op, args, stream)               \
+         : ksplit == 2 ? launch_skinny<BN_, 2, kEpi>(op, args, stream)               \
+                       : launch_skinny<BN_, 1, kEpi>(op, args, stream)
+    if (bn == 16) { ATOM_SK(16); }
+    if (bn == 32) { ATOM_SK(32); }
+    ATOM_SK(64);
+#undef ATOM_SK
+  }
 }
 
 template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
-  if (!skinny && (flags & ATOM_GEMM_FP16_PATH)) {
-    if constexpr (kO4) {
-      return launch_gemm_f16path<128, 4, 4, 16, true>(op, args, stream);     // one 128-channel head per tile
-    } else {
-      // 128 x 256 tiles once they fill the machine (converter work per MMA cycle halves), 128 x 128 below
-      const int64_t tiles256 = ((op.M + 127) / 128) * ((op.N + 255) / 256);
-      return tiles256 >= 120 ? launch_gemm_f16path<256, 3, 3, 16>(op, args, stream)
-                             : launch_gemm_f16path<128, 4, 4, 16>(op, args, stream);
-    }
-  }
   // <swap, BN, groups per pipeline stage, packed stages, K split, o4, converter warps, epilogue warpgroups>
   if (!skinny) return launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream);
+  if (op.M <= 64 && !(flags & ATOM_GEMM_LEGACY_SKINNY)) return skinny_dispatch<kO4>(op, args, flags, stream);
   // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not
   // cover the machine (the kernel is HBM-bound on the weights: more CTAs = more bytes in flight)
   const int64_t ch_tiles = (op.N + 127) / 128;
@@ -368,36 +400,6 @@ int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, const voi
                     void* d_scale, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream) {
   return gemm_common(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, d, d_scale, M, N, K,
                      flags, stream, true);
-}
-
-int atom_expand_weights_f16(const void* b, const void* b_scale, const void* b_keeper, const void* b_keeper_scale, void* out,
-                            int64_t N, int64_t K, void* stream) {
-  ATOM_REQUIRE(b && b_scale && b_keeper && b_keeper_scale && out, "expand_weights_f16: null pointer argument");
-  ATOM_REQUIRE(N > 0 && N % 8 == 0 && K >= 256 && K % 128 == 0 && N < (1ll << 31) && K < (1ll << 24),
-               "expand_weights_f16: N=%lld must be a positive multiple of 8, K=%lld a multiple of 128 >= 256", (long long)N, (long long)K);
-  ATOM_REQUIRE(aligned16(b) && aligned16(b_keeper) && aligned16(out), "expand_weights_f16: pointers must be 16-byte aligned");
-  const long long total = N * ((K - 128) / 8 + 32);
-  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
-  atom::expand_weights_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)b, (const __half*)b_scale, (const int8_t*)b_keeper,
-                                                                           (const __half*)b_keeper_scale, (__half*)out, (int)N, (int)K);
-  return check_launch("expand_weights_f16");
-}
-
-int atom_gemm_i4_o16_wx(const void* a, const void* a_scale, const void* a_keeper, const void* a_keeper_scale, const void* w_expanded,
-                        void* d, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream) {
-  (void)flags;
-  ATOM_REQUIRE(a && a_scale && a_keeper && a_keeper_scale && w_expanded && d, "gemm_i4_o16_wx: null pointer argument");
-  ATOM_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && K >= 256 && K % 128 == 0, "gemm_i4_o16_wx: bad dimensions M=%lld N=%lld K=%lld",
-               (long long)M, (long long)N, (long long)K);
-  ATOM_REQUIRE(aligned16(a) && aligned16(a_keeper) && aligned16(w_expanded) && aligned16(d), "gemm_i4_o16_wx: operand pointers must be 16-byte aligned");
-  ATOM_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 24), "gemm_i4_o16_wx: dimension too large");
-  GemmOperands op{a, w_expanded, a_keeper, nullptr, M, N, K};
-  atom::GemmArgs args{};
-  args.a_scale = (const __half*)a_scale; args.a_keeper_scale = (const __half*)a_keeper_scale;
-  args.d = (__half*)d; args.M = (int)M; args.N = (int)N; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M);
-  const int64_t tiles256 = ((M + 127) / 128) * ((N + 255) / 256);
-  return tiles256 >= 120 ? launch_gemm_f16path_wx<256, 3, 4, 16>(op, args, (cudaStream_t)stream)
-                         : launch_gemm_f16path_wx<128, 4, 5, 16>(op, args, (cudaStream_t)stream);
 }
 
 static int kv_check(const char* what, const void* data, const void* param, const void* indptr, const void* indices,

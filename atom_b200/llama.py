@@ -11,7 +11,6 @@ Differences (documented in DESIGN.md):
     num_hidden_layers / rms_norm_eps / vocab_size works as `config` (LlamaConfig does).
 """
 import math
-import os
 from dataclasses import dataclass
 
 import torch
@@ -20,11 +19,6 @@ from torch import nn
 from . import ops
 from .cat_tensor import BatchLenInfo
 from .kvcache import BatchedKvCacheInt4
-
-
-# opt-in: prefill-sized GEMMs go through the experimental FP16-path kernel (ops.GEMM_FP16_PATH; the library ignores the
-# flag for decode-sized M)
-_FP16_PATH = os.environ.get("ATOM_B200_FP16_PATH") == "1"
 
 
 @dataclass
@@ -69,15 +63,6 @@ class LinearInt4(nn.Module):
         self.scale_int4 = nn.Parameter(torch.empty((in_features // gs - 1, ops.scale_size(out_features)), dtype=torch.float16), requires_grad=False)
         self.scale_int8 = nn.Parameter(torch.empty(ops.scale_size(out_features), dtype=torch.float16), requires_grad=False)
         self.register_parameter("bias", None)
-        self._w_fp16 = None       # optional prefill cache, see expand_for_prefill()
-
-    @torch.no_grad()
-    def expand_for_prefill(self):
-        """EXPERIMENTAL: keep an FP16 expansion of the weights (4x the INT4 footprint) so that prefill-sized GEMMs only
-        convert the activations in the kernel (ops.dense_layer_gemm_i4_fp16_wx).  Decode-sized calls are unaffected."""
-        if self.out_dtype == "fp16":
-            self._w_fp16 = ops.expand_weights_f16(self.weight_int4, self.scale_int4, self.weight_int8, self.scale_int8)
-        return self
 
     @torch.no_grad()
     def init_random(self, seed=0):
@@ -93,11 +78,7 @@ class LinearInt4(nn.Module):
 
     def forward(self, input, flags=ops.GEMM_AUTO):
         outlier, norms, outlier_scales, norm_scales = input
-        if self._w_fp16 is not None and norms.shape[0] > 64:
-            return ops.dense_layer_gemm_i4_fp16_wx(norms, norm_scales, outlier, outlier_scales, self._w_fp16)
         f = {"int4": ops.dense_layer_gemm_i4_o4, "fp16": ops.dense_layer_gemm_i4_fp16}[self.out_dtype]
-        if _FP16_PATH:
-            flags |= ops.GEMM_FP16_PATH
         return f(norms, self.weight_int4, norm_scales, self.scale_int4, outlier, self.weight_int8, outlier_scales, self.scale_int8,
                  flags=flags)
 

@@ -17,7 +17,7 @@ __all__ = [
 
 GEMM_AUTO, GEMM_NO_SPLITK, GEMM_FORCE_TALL, GEMM_FORCE_SKINNY = 0, 1, 2, 4
 GEMM_SPLITK2, GEMM_SPLITK4 = 16, 32
-GEMM_FP16_PATH = 64       # experimental prefill path, see include/atom_b200.h
+GEMM_LEGACY_SKINNY = 128  # decode shapes: the round-1 kernel, kept for A/B timing
 
 
 def _stream(t):
@@ -134,34 +134,6 @@ def dense_layer_gemm_i4_o4(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_
                                               b_keeper_scale.data_ptr(), d.data_ptr(), d_scale.data_ptr(), m, n, k,
                                               flags, _stream(a)), "dense_layer_gemm_i4_o4")
     return d, d_scale
-
-
-def expand_weights_f16(b, b_scale, b_keeper, b_keeper_scale):
-    """EXPERIMENTAL (no reference counterpart): FP16 expansion of a LinearInt4's weights for dense_layer_gemm_i4_fp16_wx --
-    f16 [N, K] in the FP16-path kernel's element order, values w * scale * 2^8.  4x the INT4 footprint: a prefill cache."""
-    _req_cuda(b, b_scale, b_keeper, b_keeper_scale)
-    n, k = b.size(0), b.size(1) * 2 + b_keeper.size(1)
-    out = torch.empty((n, k), dtype=torch.float16, device=b.device)
-    with torch.cuda.device(b.device):
-        _lib.check(_lib.lib().atom_expand_weights_f16(b.data_ptr(), b_scale.data_ptr(), b_keeper.data_ptr(), b_keeper_scale.data_ptr(),
-                                                      out.data_ptr(), n, k, _stream(b)), "expand_weights_f16")
-    return out
-
-
-def dense_layer_gemm_i4_fp16_wx(a, a_scale, a_keeper, a_keeper_scale, w_expanded, flags=GEMM_AUTO):
-    """EXPERIMENTAL: dense_layer_gemm_i4_fp16 on weights expanded by expand_weights_f16 (prefill sizes; within 1e-3 of the
-    reference, not bit-identical)."""
-    _req_cuda(a, a_scale, a_keeper, a_keeper_scale, w_expanded)
-    m, n = a.size(0), w_expanded.size(0)
-    k = a.size(1) * 2 + a_keeper.size(1)
-    if w_expanded.dtype != torch.float16 or w_expanded.size(1) != k:
-        raise RuntimeError("dense_layer_gemm_i4_fp16_wx: w_expanded must be float16 [N, K]")
-    d = torch.empty((m, n), dtype=torch.float16, device=a.device)
-    with torch.cuda.device(a.device):
-        _lib.check(_lib.lib().atom_gemm_i4_o16_wx(a.data_ptr(), a_scale.data_ptr(), a_keeper.data_ptr(), a_keeper_scale.data_ptr(),
-                                                  w_expanded.data_ptr(), d.data_ptr(), m, n, k, flags, _stream(a)),
-                   "dense_layer_gemm_i4_fp16_wx")
-    return d
 
 
 def _kv_dims(kv):

@@ -42,8 +42,7 @@ extern "C" {
 #define ATOM_GEMM_FORCE_SKINNY 4u /* channels on the MMA-M axis (requires M <= 128 per tile; any M works) */
 #define ATOM_GEMM_SPLITK2 16u     /* decode shapes: force a 2-way K split (default: chosen from the tile count) */
 #define ATOM_GEMM_SPLITK4 32u     /* decode shapes: force a 4-way K split */
-#define ATOM_GEMM_FP16_PATH 64u   /* EXPERIMENTAL, M > 64 only (o16 and o4): scales applied to the operands, FP16 tensor path, one
-                                     FP32 accumulation over K -- within 1e-3 of the reference, not bit-identical */
+#define ATOM_GEMM_LEGACY_SKINNY 128u /* decode shapes: the round-1 kernel (weights expanded into shared memory), kept for A/B timing */
 
 ATOM_API int atom_version(void);
 ATOM_API const char* atom_last_error(void);
@@ -82,15 +81,6 @@ ATOM_API int atom_gemm_i4_o16(const void* a, const void* b, const void* a_scale,
 ATOM_API int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
                     const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d,
                     void* d_scale, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream);
-
-/* EXPERIMENTAL (no reference counterpart; not yet run on hardware).  Prefill acceleration cache: expand a LinearInt4's
- * weights once to FP16, W'[n][k'] = fp16(w * fp16(scale * 2^8)) in the FP16-path GEMM's element order (out: f16 [N, K]), ... */
-ATOM_API int atom_expand_weights_f16(const void* b, const void* b_scale, const void* b_keeper, const void* b_keeper_scale,
-                            void* out, int64_t N, int64_t K, void* stream);
-/* ... and run dense_layer_gemm_i4_fp16 on them: only the activations are converted in the kernel (same numerics as
- * ATOM_GEMM_FP16_PATH: within 1e-3 of the reference, not bit-identical).  d f16 [M, N]. */
-ATOM_API int atom_gemm_i4_o16_wx(const void* a, const void* a_scale, const void* a_keeper, const void* a_keeper_scale,
-                        const void* w_expanded, void* d, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream);
 
 /* Debug aid (no reference counterpart): when non-NULL, every GEMM CTA writes 128 clock64() stamps of its pipeline
  * stages to device_buffer[cta*128 ...] (layout in gemm_i4_sm100.cuh).  NULL switches tracing off. */

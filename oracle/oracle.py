@@ -147,46 +147,6 @@ def batch_decode_i4(q, data, param, indptr, indices, last_off, layer):
 
 # ----------------------------------------------------------------------------------------------
 # helpers shared by tests / bench to build synthetic quantised operands (SURVEY 8d "C2 inputs")
-def gemm_i4_o16_f16path_model(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale):
-    """Numerical MODEL (numpy) of the experimental FP16-path GEMM (atom_b200/csrc/gemm_f16path_sm100.cuh), not of the
-    reference: operands a' = fp16(a*sA[m,g]), b' = fp16(b*fp16(sB[n,g]*256)) -- one correctly rounded product each, exactly what
-    w4_f16_convert.cuh produces -- exact products, one FP32 accumulation over all of K (float64 here: the tensor core's
-    summation order is unspecified), * 2^-8, RN to half.  Uses sB[n] for column n (no column pairing): equals the
-    reference's arithmetic up to operand rounding whenever the B scales are pair-shared."""
-    t, m, n, k = _gemm_args(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale)
-    a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale = t
-    g = k // 128 - 1
-    f32, f16 = np.float32, np.float16
-    a4 = unpack_int4(a).astype(f32).reshape(m, g, 128)
-    b4 = unpack_int4(b).astype(f32).reshape(n, g, 128)
-    sa = a_scale_from_layout(a_scale.reshape(g, -1), m).astype(f32)                    # [G, M]
-    sak = a_scale_from_layout(a_keeper_scale, m).astype(f32)
-    sb = (b_scale.reshape(-1)[: g * n].reshape(g, n).astype(f32) * 256).astype(f16).astype(f32)
-    sbk = (b_keeper_scale[:n].astype(f32) * 256).astype(f16).astype(f32)
-    ap = (a4 * sa.T[:, :, None]).astype(f16).reshape(m, -1)
-    bp = (b4 * sb.T[:, :, None]).astype(f16).reshape(n, -1)
-    akp = (a_keeper.astype(f32) * sak[:, None]).astype(f16)
-    bkp = (b_keeper.astype(f32) * sbk[:, None]).astype(f16)
-    af = np.concatenate([ap, akp], 1).astype(np.float64)
-    bf = np.concatenate([bp, bkp], 1).astype(np.float64)
-    return ((af @ bf.T).astype(f32) * f32(1.0 / 256.0)).astype(f16)
-
-
-def expand_weights_f16_model(b, b_scale, b_keeper, b_keeper_scale):
-    """numpy model of atom_expand_weights_f16: f16 [N, K], each 8-element chunk in the converter's order
-    [e0 e4 e1 e5 e2 e6 e3 e7] (keeper columns in natural order), values fp16(w * fp16(scale * 256))."""
-    b, b_keeper = _c(b, np.uint8), _c(b_keeper, np.int8)
-    n, g = b.shape[0], b.shape[1] // 64
-    f32, f16 = np.float32, np.float16
-    sb = (_c(b_scale, np.float16).reshape(-1)[: g * n].reshape(g, n).astype(f32) * 256).astype(f16).astype(f32)
-    sbk = (_c(b_keeper_scale, np.float16)[:n].astype(f32) * 256).astype(f16).astype(f32)
-    w = unpack_int4(b).astype(f32).reshape(n, g, 128) * sb.T[:, :, None]
-    w = w.astype(f16).reshape(n, g * 16, 8)[:, :, [0, 4, 1, 5, 2, 6, 3, 7]].reshape(n, g * 128)
-    wk = (b_keeper.astype(f32) * sbk[:, None]).astype(f16)
-    return np.concatenate([w, wk], 1)
-
-
-# ----------------------------------------------------------------------------------------------
 def pack_int4(q):
     """q: int array [-8,7], last dim even -> uint8 packed low-nibble-first (Reorder.cuh:16-19)."""
     q = np.asarray(q).astype(np.int16)

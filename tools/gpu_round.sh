@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU visit (1 GPU): everything a round needs, each step under its own timeout, everything into gpurun_out/.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [steps...]'
-# steps (default: tests smoke bench gtime trace layer harness micro; extra: exp = the never-executed experimental pieces)
+# steps (default: tests smoke bench gtime trace layer harness micro; extra: sk = decode-GEMM development loop)
 set -u
 mkdir -p gpurun_out
 OUT=gpurun_out
@@ -21,9 +21,13 @@ for s in $STEPS; do case $s in
            timeout 300 python tools/layer_bench.py --hidden 5120 --inter 13824 --heads 40 --batch 32 --kvlen 1024 --layers 40 2>&1 | tail -1 | tee $OUT/layer_13b.json ;;
   harness) echo "== continuous-batching harness"; timeout 900 python tools/bench_textgen.py --model 7b --batch-size 16 --num-batches 2 --maxlen 512 2> $OUT/textgen.err | tee $OUT/textgen_7b.txt | tail -9; tail -3 $OUT/textgen.err ;;
   micro)   echo "== microbenchmarks"; for b in microbench sync_bench tma_bench tmem_bench; do timeout 120 ./tools/$b > $OUT/$b.jsonl 2>&1; echo "$b rc=$?"; done ;;
-  exp)     echo "== experimental: FP16-path GEMM, PDL (opt-in tests, then timings)"
-           ATOM_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_z_f16path_gpu.py tests/test_z_pdl_gpu.py -m gpu -q -x --timeout=300 -p no:cacheprovider > $OUT/pytest_exp.txt 2>&1; echo "rc=$?"; tail -25 $OUT/pytest_exp.txt
-           ATOM_EXPERIMENTAL=1 timeout 600 python tools/gpu_check.py gtime 256 1024 4096 2> $OUT/gtime_exp.err | tee $OUT/gtime_exp.jsonl; tail -3 $OUT/gtime_exp.err
-           ATOM_B200_PDL=1 timeout 300 python tools/layer_bench.py 2>&1 | tail -1 | tee $OUT/layer_7b_pdl.json ;;
+  sk)      echo "== skinny GEMM: probes, parity, timing (PDL on / off, legacy kernel beside it)"
+           timeout 300 python tools/gpu_check.py diag 2>&1 | tee $OUT/sk_diag.jsonl | cut -c1-400
+           timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py -m gpu -q -x --timeout=300 -p no:cacheprovider -k "gemm" > $OUT/pytest_sk.txt 2>&1; echo "rc=$?"; tail -12 $OUT/pytest_sk.txt
+           timeout 300 python tools/gpu_check.py gtime 16 32 64 2> $OUT/sk_gtime.err | tee $OUT/sk_gtime.jsonl; tail -3 $OUT/sk_gtime.err
+           ATOM_B200_GEMM_PDL=0 timeout 300 python tools/gpu_check.py gtime 16 2>> $OUT/sk_gtime.err | tee $OUT/sk_gtime_nopdl.jsonl
+           timeout 300 python tools/gpu_check.py gshape 2>> $OUT/sk_gtime.err | tee $OUT/sk_gshape.jsonl
+           : > $OUT/sk_trace.jsonl
+           for cfg in "16 0" "16 1"; do timeout 120 python tools/gpu_check.py trace $cfg 2>&1 | tail -1 | tee -a $OUT/sk_trace.jsonl | cut -c1-2500; done ;;
   *) echo "unknown step $s" ;;
 esac; done
