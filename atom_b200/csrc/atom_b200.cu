@@ -223,11 +223,9 @@ int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream
   int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (skinny)");
   if (rc) return rc;
   const uint64_t kp = (uint64_t)(op.K - 128) / 2;
-  CUtensorMap tp4, tq4, tp8, tq8;
+  CUtensorMap tp4, tp8;       // weights only: the token operand is read with plain loads (no descriptor per activation buffer)
   if ((rc = make_map(&tp4, op.b, kp, op.N, kp, 64, C::BM, 2))) return rc;
-  if ((rc = make_map(&tq4, op.a, kp, op.M, kp, 64, BN, 0))) return rc;
   if ((rc = make_map(&tp8, op.bk, 128, op.N, 128, 128, C::BM, 1))) return rc;
-  if ((rc = make_map(&tq8, op.ak, 128, op.M, 128, 128, BN, 1))) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)((op.N + C::BM - 1) / C::BM), (unsigned)((op.M + BN - 1) / BN), kSplit);
   cfg.blockDim = dim3(C::THREADS);
@@ -243,7 +241,7 @@ int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tp4, tq4, tp8, tq8, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tp4, tp8, args);
   if (e != cudaSuccess) return fail(ATOM_E_CUDA, "gemm_i4 (skinny) launch: %s", cudaGetErrorString(e));
   return ATOM_OK;
 }
@@ -331,6 +329,7 @@ int gemm_common(const void* a, const void* b, const void* a_scale, const void* b
   args.a_keeper_scale = (const __half*)a_keeper_scale; args.b_keeper_scale = (const __half*)b_keeper_scale;
   args.d = o4 ? nullptr : (__half*)d; args.d4 = o4 ? (uint8_t*)d : nullptr; args.d_scale = (__half2*)d_scale;
   args.M = (int)M; args.N = (int)N; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M); args.trace = g_trace;
+  args.a4 = (const uint8_t*)a; args.a8 = (const int8_t*)a_keeper;
   return o4 ? gemm_dispatch<true>(op, args, flags, (cudaStream_t)stream) : gemm_dispatch<false>(op, args, flags, (cudaStream_t)stream);
 }
 

@@ -6,22 +6,27 @@
 // /root/reference/e2e/punica-atom/punica/ops/csrc/GEMM/DenseLayerGEMM_i4_o4.cu:440-787): exact INT32 group sums, one
 // FP16 multiply of the two scales, FP32 fma accumulation in group order, keeper last, RN cast to half.
 //
-// A decode GEMM is a weight stream: 9 MB at M=16, N=K=4096 against 0.5 GOP.  What bounded the first design
-// (profiles/r01_gemm_pipeline_trace_final.jsonl) was not bandwidth but the latency chain
-//   TMA -> converter (LDS, expand, STS, proxy fence) -> MMA -> commit -> converter may reuse the 16 KB operand slot
-// with only two operand slots per CTA and one CTA per SM (150 KB of shared memory, most of it expanded INT8 weights).
-// Here:
-//   * TMA lands packed INT4 weight tiles (64 B rows, SWIZZLE_64B so that a warp reading one 16-B chunk per ROW is
-//     conflict free) in a 6-deep ring;
-//   * converter thread r owns weight row r of the tile: 4 x LDS.128 -> 48 ALU ops -> ONE tcgen05.st (32 columns) puts
-//     the row's 128 INT8 values (value * 16) into a tensor-memory operand slot -- no shared-memory store, no swizzle
-//     arithmetic, no generic->async proxy fence for the big operand, and half the shared-memory traffic;
-//   * tcgen05.mma.kind::i8 reads A from tensor memory (TS form) and the (tiny) token operand from shared memory;
-//   * shared memory per CTA drops to ~90 KB and tensor memory to 256 columns, so TWO CTAs are resident per SM: with
-//     programmatic dependent launch the next GEMM's CTAs start streaming their weights while this one drains its
-//     epilogue (griddepcontrol: weights do not depend on the preceding kernel, activations and the output do);
-//   * K may be split over a cluster of 2 or 4 CTAs; every rank reduces and stores its own slice of the token columns
-//     (partials pushed through DSMEM, summed in rank order: deterministic).
+// A decode GEMM is a weight stream (9 MB at M=16, N=K=4096 against 0.5 GOP) followed by a short dependent tail.
+// Measured (profiles/r01_gemm_pipeline_trace_final.jsonl, r02_gemm_skinny_v2_pipeline_trace.jsonl): the stream itself is
+// cheap; what costs is (1) everything that is serialised behind the arrival of the ACTIVATIONS -- they are the output of
+// the kernel in front, so under programmatic dependent launch that part cannot overlap it -- and (2) fixed per-CTA
+// latencies.  Hence two decoupled pipelines:
+//
+//   WEIGHTS (no dependency on the preceding kernel; start at CTA launch)
+//     TMA: packed INT4 tiles (64 B rows, SWIZZLE_64B => a warp reading one 16-B chunk per ROW is conflict free), 6-deep ring
+//     converter thread r owns weight row r: 4 x LDS.128 -> 48 ALU ops -> ONE tcgen05.st (32 columns) puts the row's 128
+//       INT8 values (value * 16) into a tensor-memory operand slot: no shared-memory store, no swizzle arithmetic, no
+//       proxy fence, half the shared-memory traffic.  Up to 6 groups wait converted in tensor memory, 6 more packed in smem.
+//   ACTIVATIONS (after griddepcontrol.wait)
+//     two warps read the packed token tile straight from global memory (L2: it was just written), expand it into the
+//       canonical K-major SWIZZLE_128B INT8 operand in shared memory, four groups per hand-off;
+//     the epilogue warps stage the scale rows themselves (no loader warp, no scale ring);
+//     tcgen05.mma.kind::i8, A from tensor memory (TS form), B = tokens from shared memory; INT32 accumulators in TMEM;
+//     epilogue: tcgen05.ld -> acc = fmaf(float(c), float(hmul(sA, sB)), acc); split-K partials go to the rank that owns
+//       the token columns with st.async (data + mbarrier complete_tx in one message: no cluster barrier on the path),
+//       are summed in rank order (deterministic) and stored by that rank.
+//   Shared memory ~100 KB and 256 tensor-memory columns per CTA => TWO CTAs per SM: the next GEMM's CTAs stream and
+//   convert their weights while this one waits for its activations or drains its tail.
 #pragma once
 #include "gemm_i4_sm100.cuh"
 
@@ -32,36 +37,38 @@ enum { EPI_O16 = 0, EPI_O4 = 1 };
 template <int BN, int kSplit, int kEpi>
 struct SkinnyCfg {
   static constexpr int BM = 128;                       // weight rows per tile = TMEM lanes
-  static constexpr int A_RING = 4;                     // tensor-memory operand slots, 32 columns (one group) each
-  static constexpr int ACC = 128 / BN;                 // accumulator slots of BN columns: 8 / 4 / 2
-  static constexpr int NB = A_RING > ACC ? A_RING : ACC;   // "group's MMAs completed" barriers
+  static constexpr bool ONE_PER_SM = BN == 64;         // 64 accumulators per thread need > 80 registers
+  static constexpr int TMEM_COLS = ONE_PER_SM ? 512 : 256;
+  static constexpr int A_RING = ONE_PER_SM ? 8 : 6;    // tensor-memory operand slots, 32 columns (one group) each
+  static constexpr int ACC = ONE_PER_SM ? 4 : 64 / BN; // accumulator slots of BN columns
+  static constexpr int NB = A_RING;                    // "group's MMAs completed" barriers (>= ACC)
   static constexpr int A_COL0 = 0, ACC_COL0 = A_RING * 32;
-  static constexpr int TMEM_COLS = 256;
-  static constexpr int PACK = BN == 16 ? 6 : (BN == 32 ? 5 : 4);   // packed ring depth (groups)
-  static constexpr int SCALE_SLOTS = 8;
+  static constexpr int PACK = ONE_PER_SM ? 8 : (BN == 16 ? 6 : 5);   // packed weight ring depth (groups)
+  static constexpr int QB = 4, QS = 2 * QB;            // token tiles: groups per hand-off, expanded slots
+  static constexpr int SC = BN == 16 ? 32 : 16;        // groups per staged scale chunk
   static constexpr int THREADS = 384;                  // 4 service warps, 4 converter warps, 4 epilogue warps
-  static constexpr int PACK_P = BM * 64, PACK_Q = BN * 64;
+  static constexpr int PACK_P = BM * 64;
   static constexpr int EXP_Q = (BN * 128 + 1023) / 1024 * 1024;
   static constexpr int CPR = BN / kSplit;              // token columns reduced + stored by one split-K rank
   static constexpr int OFF_PACK_P = 0;
   static constexpr int OFF_EXP_Q = OFF_PACK_P + PACK * PACK_P;
-  static constexpr int OFF_KEEP_P = OFF_EXP_Q + A_RING * EXP_Q;
+  static constexpr int OFF_KEEP_P = OFF_EXP_Q + QS * EXP_Q;
   static constexpr int OFF_KEEP_Q = OFF_KEEP_P + BM * 128;
-  static constexpr int OFF_PACK_Q = OFF_KEEP_Q + EXP_Q;
-  static constexpr int OFF_SM = OFF_PACK_Q + PACK * PACK_Q;
-  static constexpr int RED_BYTES = BM * CPR * 4;       // one source rank's partial for this rank's columns
-  static constexpr int OFF_RED = OFF_SM + SCALE_SLOTS * 512;
+  static constexpr int OFF_SB = OFF_KEEP_Q + EXP_Q;                    // [SC][128] weight-scale halves
+  static constexpr int OFF_SA = OFF_SB + SC * 256;                     // [SC][BN/2] (lower, upper) activation-scale words
+  static constexpr int RED_BYTES = BM * CPR * 4;                       // one source rank's partial for this rank's columns
+  static constexpr int OFF_RED = OFF_SA + SC * BN * 2;
   static constexpr int OFF_XCH = OFF_RED + (kSplit > 1 ? (kSplit - 1) * RED_BYTES : 0);   // o4: per-warp |v| min/max
   static constexpr int OFF_BAR = OFF_XCH + (kEpi == EPI_O4 ? 8 * BN * 4 : 0);
-  static constexpr int NUM_BARS = 2 * PACK + A_RING + NB + ACC + 2 * SCALE_SLOTS + 1;
+  static constexpr int NUM_BARS = 2 * PACK + A_RING + 2 + NB + ACC + 3;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
-  static constexpr int CTAS_PER_SM = SMEM_BYTES <= 112 * 1024 ? 2 : 1;
+  static constexpr int CTAS_PER_SM = ONE_PER_SM ? 1 : 2;
   static_assert(BN == 16 || BN == 32 || BN == 64, "token tile");
   static_assert(BN % kSplit == 0 && CPR >= 4, "every split-K rank owns at least 4 token columns");
   static_assert(kEpi == EPI_O16 || kSplit == 1, "the INT4-output epilogue quantises un-split FP32 sums");
   static_assert(A_RING * 32 + ACC * BN <= TMEM_COLS, "tensor memory budget");
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(ONE_PER_SM ? SMEM_BYTES <= 227 * 1024 : SMEM_BYTES <= 113 * 1024, "shared memory budget (two CTAs per SM)");
 };
 
 // tcgen05.mma, A operand in tensor memory, B through a shared-memory descriptor
@@ -85,36 +92,36 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void st_dsmem_v4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// 16 bytes into a peer CTA's shared memory; the same message completes 16 transaction bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float b, float c, float d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar) : "memory");
 }
 
 template <int BN, int kSplit, int kEpi>
 __global__ void __launch_bounds__(SkinnyCfg<BN, kSplit, kEpi>::THREADS, SkinnyCfg<BN, kSplit, kEpi>::CTAS_PER_SM)
 gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 weights   (box 64 B x 128 rows, SWIZZLE_64B)
-                      const __grid_constant__ CUtensorMap tm_q4,   // packed INT4 tokens    (box 64 B x BN rows)
                       const __grid_constant__ CUtensorMap tm_p8,   // INT8 keeper weights   (box 128 B x 128 rows, SWIZZLE_128B)
-                      const __grid_constant__ CUtensorMap tm_q8,   // INT8 keeper tokens    (box 128 B x BN rows, SWIZZLE_128B)
                       const GemmArgs args) {
   using C = SkinnyCfg<BN, kSplit, kEpi>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* pack_full = bars;                           // TMA landed a group's packed tiles                 (1 + tx)
-  uint64_t* pack_empty = pack_full + C::PACK;           // the converter warps have read them                (4)
-  uint64_t* a_full = pack_empty + C::PACK;              // operand slot written: TMEM weights + smem tokens  (4)
-  uint64_t* mma_done = a_full + C::A_RING;              // the group's MMAs completed (tcgen05.commit)       (1)
-  uint64_t* acc_empty = mma_done + C::NB;               // epilogue has read the accumulator slot            (4)
-  uint64_t* scale_full = acc_empty + C::ACC;            // the group's scales landed (cp.async, no-inc)      (32)
-  uint64_t* scale_empty = scale_full + C::SCALE_SLOTS;  //                                                   (4)
-  uint64_t* keep_full = scale_empty + C::SCALE_SLOTS;   // INT8 keeper operands landed                       (1 + tx)
+  uint64_t* pack_full = bars;                           // TMA landed a group's packed weight tile            (1 + tx)
+  uint64_t* pack_empty = pack_full + C::PACK;           // the converter warps have read it                   (4)
+  uint64_t* a_full = pack_empty + C::PACK;              // tensor-memory operand slot written                 (4)
+  uint64_t* qx_full = a_full + C::A_RING;               // a batch of QB expanded token tiles is in place     (2)
+  uint64_t* mma_done = qx_full + 2;                     // the group's MMAs completed (tcgen05.commit)        (1)
+  uint64_t* acc_empty = mma_done + C::NB;               // epilogue has read the accumulator slot             (4)
+  uint64_t* keep_full = acc_empty + C::ACC;             // INT8 keeper weights landed                         (1 + tx)
+  uint64_t* kq_full = keep_full + 1;                    // INT8 keeper tokens copied                          (2)
+  uint64_t* red_full = kq_full + 1;                     // split-K: every peer's partial has arrived          (1 + tx)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p0 = blockIdx.x * C::BM;        // first weight row (output channel) of the tile
-  const int q0 = blockIdx.y * BN;           // first token
-  const int m0 = q0, n0 = p0;
+  const int n0 = blockIdx.x * C::BM;        // first weight row (output channel) of the tile
+  const int m0 = blockIdx.y * BN;           // first token
 
   const int total_groups = args.G + 1;      // index G = INT8 keeper
   int g_begin = 0, g_end = total_groups;
@@ -130,56 +137,52 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   if (threadIdx.x == 0) { griddep_launch_dependents(); trace_stamp(args, 0); }
 
   // ---------------------------------------------------------------- setup
-  // part 1 = weight tile (independent of the preceding kernel), part 2 = token tile
-  auto issue_group = [&](int i, int part) {
-    const int ps = i % C::PACK, g = g_begin + i;
-    if (part & 1) {
-      mbar_arrive_expect_tx(&pack_full[ps], C::PACK_P + C::PACK_Q);
-      tma_load_2d(smem + C::OFF_PACK_P + ps * C::PACK_P, &tm_p4, &pack_full[ps], g * 64, p0);
-    }
-    if (part & 2) tma_load_2d(smem + C::OFF_PACK_Q + ps * C::PACK_Q, &tm_q4, &pack_full[ps], g * 64, q0);
-    if (i < 16 && (part & 2)) trace_stamp(args, 8 + i);
-  };
-  const int first = min(C::PACK, n4);
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_p4); tma_prefetch_desc(&tm_q4);
+    tma_prefetch_desc(&tm_p4);
     for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_full[i], 1);
     mbar_init(keep_full, 1);
     fence_barrier_init();
-    // weights first: they do not depend on the preceding kernel, so under programmatic dependent launch they stream
-    // (and are converted) while that kernel is still running
-    for (int i = 0; i < first; ++i) issue_group(i, 1);
+    // the weight stream starts before anything else exists: it depends on nothing
+    const int first = min(C::PACK, n4);
+    for (int i = 0; i < first; ++i) {
+      mbar_arrive_expect_tx(&pack_full[i], C::PACK_P);
+      tma_load_2d(smem + C::OFF_PACK_P + i * C::PACK_P, &tm_p4, &pack_full[i], (g_begin + i) * 64, n0);
+      if (i < 16) trace_stamp(args, 8 + i);
+    }
     if (n4 < iters) {                                                  // this rank owns the keeper group
-      tma_prefetch_desc(&tm_p8); tma_prefetch_desc(&tm_q8);
-      mbar_arrive_expect_tx(keep_full, C::BM * 128 + BN * 128);
-      tma_load_2d(smem + C::OFF_KEEP_P, &tm_p8, keep_full, 0, p0);
+      tma_prefetch_desc(&tm_p8);
+      mbar_arrive_expect_tx(keep_full, C::BM * 128);
+      tma_load_2d(smem + C::OFF_KEEP_P, &tm_p8, keep_full, 0, n0);
     }
   } else if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_empty[i], 4);
     for (int i = 0; i < C::A_RING; ++i) mbar_init(&a_full[i], 4);
+    mbar_init(&qx_full[0], 2); mbar_init(&qx_full[1], 2);
     for (int i = 0; i < C::NB; ++i) mbar_init(&mma_done[i], 1);
     for (int i = 0; i < C::ACC; ++i) mbar_init(&acc_empty[i], 4);
-    for (int i = 0; i < C::SCALE_SLOTS; ++i) { mbar_init(&scale_full[i], 32); mbar_init(&scale_empty[i], 4); }
+    mbar_init(kq_full, 2);
+    mbar_init(red_full, 1);
     fence_barrier_init();
+    if constexpr (kSplit > 1) mbar_arrive_expect_tx(red_full, (kSplit - 1) * C::RED_BYTES);
   } else if (warp == 2) {
     tmem_alloc<C::TMEM_COLS>(tmem_ptr);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if constexpr (kSplit > 1) cluster_arrive_relaxed();                  // see the reduction: remote smem needs a running CTA
+  if constexpr (kSplit > 1) cluster_arrive_relaxed();                  // peers may write our smem once we are running
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) trace_stamp(args, 1);
 
   if (warp == 0) {
-    // ============================================================ TMA producer
+    // ============================================================ weight TMA producer
     if (lane == 0) {
-      griddep_wait();                                                  // activations are the preceding kernel's output
-      for (int i = 0; i < first; ++i) issue_group(i, 2);
-      if (n4 < iters) tma_load_2d(smem + C::OFF_KEEP_Q, &tm_q8, keep_full, 0, q0);
-      for (int i = first; i < n4; ++i) {
-        mbar_wait(&pack_empty[i % C::PACK], ((i / C::PACK) & 1) ^ 1);
-        issue_group(i, 3);
+      for (int i = C::PACK; i < n4; ++i) {
+        const int ps = i % C::PACK;
+        mbar_wait(&pack_empty[ps], ((i / C::PACK) & 1) ^ 1);
+        mbar_arrive_expect_tx(&pack_full[ps], C::PACK_P);
+        tma_load_2d(smem + C::OFF_PACK_P + ps * C::PACK_P, &tm_p4, &pack_full[ps], (g_begin + i) * 64, n0);
+        if (i < 16) trace_stamp(args, 8 + i);
       }
     }
   } else if (warp == 1) {
@@ -191,16 +194,18 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
         if (i >= C::ACC) mbar_wait(&acc_empty[as], ((i / C::ACC) - 1) & 1);
         const uint32_t d_tmem = tmem_base + C::ACC_COL0 + as * BN;
         if (i < n4) {
-          const int ar = i % C::A_RING;
+          const int ar = i % C::A_RING, b = i / C::QB;
+          if (i % C::QB == 0) mbar_wait(&qx_full[b & 1], (b >> 1) & 1);
           mbar_wait(&a_full[ar], (i / C::A_RING) & 1);
           tc_fence_after();
           if (i < 16) trace_stamp(args, 88 + i);
-          const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + ar * C::EXP_Q));
+          const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + (i % C::QS) * C::EXP_Q));
 #pragma unroll
           for (int k = 0; k < 4; ++k)        // 4 x K=32: 8 tensor-memory columns of A, 32 B of each token row
             umma_i8_ts(d_tmem, tmem_base + C::A_COL0 + ar * 32 + k * 8, dq + (uint64_t)(k * 2), idesc, k > 0);
         } else {
           mbar_wait(keep_full, 0);
+          mbar_wait(kq_full, 0);
           tc_fence_after();
           if (i < 16) trace_stamp(args, 88 + i);
           const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + C::OFF_KEEP_P));
@@ -208,36 +213,79 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_i8(d_tmem, dp + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k > 0);
         }
-        umma_commit(&mma_done[i % C::NB]);   // accumulators ready AND operand slot reusable
+        umma_commit(&mma_done[i % C::NB]);   // accumulators ready AND operand slots reusable
       }
     }
-  } else if (warp == 2) {
-    // ============================================================ scale loader (cp.async into an 8-group ring)
-    // slot: [0,256) the tile's 128 weight-scale halves (thread n reads the pair word n/2); [256, ...) the (lower, upper)
-    // activation-scale words of the token rows, word = (r/16)*8 + r%8 (raw copy of the reference layout, Reorder.cuh:39-50)
-    griddep_wait();
-    for (int i = 0; i < iters; ++i) {
-      const int ss = i % C::SCALE_SLOTS, g = g_begin + i;
-      if (i >= C::SCALE_SLOTS) mbar_wait(&scale_empty[ss], ((i / C::SCALE_SLOTS) - 1) & 1);
-      const bool keeper = (g == args.G);
-      const __half* as_row = keeper ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
-      const __half* bs_row = keeper ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
-      uint8_t* slot = smem + C::OFF_SM + ss * 512;
+  } else if (warp == 2 || warp == 3) {
+    // ============================================================ token tiles: global -> INT8 operand in smem
+    // chunk c of a batch: group c / (4 BN), token row (c % (4 BN)) / 4, 16-byte piece c % 4 of the row's 64 packed bytes
+    const int tq = (warp - 2) * 32 + lane;
+    const size_t kp = (size_t)args.G * 64;                // packed bytes per token row
+    griddep_wait();                                       // the activations are the preceding kernel's output
+    if (tq == 0) trace_stamp(args, 6);
+    const int nbatch = (n4 + C::QB - 1) / C::QB;
+    for (int b = 0; b < nbatch; ++b) {
+      if (b >= 2) { const int gl = (b - 1) * C::QB - 1; mbar_wait(&mma_done[gl % C::NB], (gl / C::NB) & 1); }   // slots free
+      const int ng = min(C::QB, n4 - b * C::QB), chunks = ng * BN * 4;
+      for (int c0 = 0; c0 < chunks; c0 += 256) {
+        uint4 w[4];
 #pragma unroll
-      for (int w = lane; w < BN / 2; w += 32) {
-        const int blk = w >> 3, r = w & 7;
-        if (m0 + 16 * blk + r < args.M) cp_async_4(slot + 256 + w * 4, as_row + 64 * (m0 / 16 + blk) + 8 * r);
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * 64 + tq;
+          w[u] = make_uint4(0, 0, 0, 0);
+          if (c < chunks) {
+            const int grp = c / (BN * 4), r = (c % (BN * 4)) >> 2, j = c & 3;
+            if (m0 + r < args.M)
+              w[u] = ld_cg_v4(args.a4 + (size_t)(m0 + r) * kp + (size_t)(g_begin + b * C::QB + grp) * 64 + j * 16);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * 64 + tq;
+          if (c < chunks) {
+            const int grp = c / (BN * 4), r = (c % (BN * 4)) >> 2, j = c & 3;
+            uint4 lo, hi;
+            expand_chunk(w[u], lo, hi);
+            uint8_t* row = smem + C::OFF_EXP_Q + ((b * C::QB + grp) % C::QS) * C::EXP_Q + (r >> 3) * 1024 + (r & 7) * 128;
+            *reinterpret_cast<uint4*>(row + (((2 * j) ^ (r & 7)) << 4)) = lo;
+            *reinterpret_cast<uint4*>(row + (((2 * j + 1) ^ (r & 7)) << 4)) = hi;
+          }
+        }
       }
-      if (lane < 16 && n0 + 8 * lane < args.N) cp_async_16(slot + lane * 16, bs_row + n0 + 8 * lane);
-      cp_async_mbar_arrive_noinc(&scale_full[ss]);
+      if (b == 0 && n4 < iters) {                          // keeper tokens: plain copy into the SWIZZLE_128B layout
+        for (int c = tq; c < BN * 8; c += 64) {
+          const int r = c >> 3, j = c & 7;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (m0 + r < args.M) v = ld_cg_v4(args.a8 + (size_t)(m0 + r) * 128 + j * 16);
+          *reinterpret_cast<uint4*>(smem + C::OFF_KEEP_Q + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = v;
+        }
+      }
+      fence_proxy_async_smem();            // generic-proxy stores -> visible to the MMA's operand fetch
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&qx_full[b & 1]);
+        if (b == 0 && n4 < iters) mbar_arrive(kq_full);
+      }
+      if (tq == 0 && b == 0) trace_stamp(args, 5);
+    }
+    if (nbatch == 0 && n4 < iters) {                       // keeper-only rank
+      for (int c = tq; c < BN * 8; c += 64) {
+        const int r = c >> 3, j = c & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (m0 + r < args.M) v = ld_cg_v4(args.a8 + (size_t)(m0 + r) * 128 + j * 16);
+        *reinterpret_cast<uint4*>(smem + C::OFF_KEEP_Q + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(kq_full);
     }
   } else if (warp >= 4 && warp < 8) {
-    // ============================================================ converters: thread = weight row
+    // ============================================================ weight converters: thread = weight row
     const int wq = warp & 3, row = wq * 32 + lane, t = (warp - 4) * 32 + lane;
     const int xr = (row >> 1) & 3;                       // SWIZZLE_64B: 16-B chunk index ^= address bits [7,9)
     for (int i = 0; i < n4; ++i) {
       const int ps = i % C::PACK, ar = i % C::A_RING;
-      if (i >= C::A_RING) mbar_wait(&mma_done[(i - C::A_RING) % C::NB], ((i - C::A_RING) / C::NB) & 1);
+      if (i >= C::A_RING) mbar_wait(&mma_done[ar], ((i / C::A_RING) - 1) & 1);     // NB == A_RING
       if (t == 0 && i < 16) trace_stamp(args, 24 + i);
       mbar_wait(&pack_full[ps], (i / C::PACK) & 1);
       if (t == 0 && i < 16) trace_stamp(args, 40 + i);
@@ -245,9 +293,8 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       uint4 w[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const uint4*>(prow + ((j ^ xr) << 4));
-      // token tile -> canonical K-major SWIZZLE_128B INT8 operand in shared memory (same K permutation as below)
-      convert_tile<BN, 128>(smem + C::OFF_PACK_Q + ps * C::PACK_Q, smem + C::OFF_EXP_Q + ar * C::EXP_Q, t);
       // chunk j (32 consecutive K) -> columns 8j..8j+7: four "even element" words, then four "odd element" words
+      // (the token tiles use the same K permutation, so dot products are unchanged)
       uint32_t r[32];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -256,34 +303,57 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
         r[8 * j + 0] = lo.x; r[8 * j + 1] = lo.y; r[8 * j + 2] = lo.z; r[8 * j + 3] = lo.w;
         r[8 * j + 4] = hi.x; r[8 * j + 5] = hi.y; r[8 * j + 6] = hi.z; r[8 * j + 7] = hi.w;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pack_empty[ps]);       // the packed tile is in registers: the slot can be refilled
       tmem_st_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::A_COL0 + ar * 32), r);
       tmem_st_wait();
       if (t == 0 && i < 16) trace_stamp(args, 56 + i);
-      fence_proxy_async_smem();          // the token tile's generic-proxy stores -> visible to the MMA's operand fetch
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&pack_empty[ps]); mbar_arrive(&a_full[ar]); }
+      if (lane == 0) mbar_arrive(&a_full[ar]);
       if (t == 0 && i < 16) trace_stamp(args, 72 + i);
     }
   } else if (warp >= 8) {
     // ============================================================ epilogue: thread = output channel (TMEM lane)
-    const int wq = warp & 3, row = wq * 32 + lane;
+    const int wq = warp & 3, row = wq * 32 + lane, te = (warp - 8) * 32 + lane;
     float acc[BN];
 #pragma unroll
     for (int c = 0; c < BN; ++c) acc[c] = 0.f;
+    __half* sb_s = reinterpret_cast<__half*>(smem + C::OFF_SB);
+    uint32_t* sa_s = reinterpret_cast<uint32_t*>(smem + C::OFF_SA);
 
     for (int i = 0; i < iters; ++i) {
-      const int as = i % C::ACC, ss = i % C::SCALE_SLOTS;
+      if (i % C::SC == 0) {
+        // ---- stage the scale rows of groups [i, i + SC): weight scales first (no dependency), then activation scales
+        const int ng = min(C::SC, iters - i);
+        if (i > 0) asm volatile("bar.sync 2, 128;" ::: "memory");        // everyone is done with the previous chunk
+        for (int c = te; c < ng * 16; c += 128) {
+          const int gi = c >> 4, part = c & 15, g = g_begin + i + gi;
+          const __half* bs_row = (g == args.G) ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (n0 + 8 * part < args.N) v = ld_nc_v4(bs_row + n0 + 8 * part);
+          reinterpret_cast<uint4*>(sb_s)[c] = v;
+        }
+        if (i == 0) griddep_wait();
+        for (int c = te; c < ng * (BN / 2); c += 128) {
+          const int gi = c / (BN / 2), w = c % (BN / 2), blk = w >> 3, r = w & 7, g = g_begin + i + gi;
+          const __half* as_row = (g == args.G) ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
+          uint32_t v = 0;
+          if (m0 + 16 * blk + r < args.M) v = ld_cg_u32(as_row + 64 * (m0 / 16 + blk) + 8 * r);
+          sa_s[c] = v;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (te == 0 && i == 0) trace_stamp(args, 7);
+      }
+      const int as = i % C::ACC, si = i % C::SC;
       const bool keeper = (g_begin + i == args.G);
-      mbar_wait(&scale_full[ss], (i / C::SCALE_SLOTS) & 1);
+      const __half2 sm2 = reinterpret_cast<const __half2*>(sb_s + si * 128)[row >> 1];   // {sB[n & ~1], sB[n | 1]}
+      const __half2* snw = reinterpret_cast<const __half2*>(sa_s + si * (BN / 2));       // (sA[tok], sA[tok + 8]) words
       mbar_wait(&mma_done[i % C::NB], (i / C::NB) & 1);
       tc_fence_after();
       if (warp == 8 && lane == 0 && i < 16) trace_stamp(args, 104 + i);
-      const uint8_t* slot = smem + C::OFF_SM + ss * 512;
-      const __half2 sm2 = reinterpret_cast<const __half2*>(slot)[row >> 1];          // {sB[n & ~1], sB[n | 1]}
-      const __half2* snw = reinterpret_cast<const __half2*>(slot + 256);             // (sA[tok], sA[tok + 8]) words
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::ACC_COL0 + as * BN);
-      constexpr int CH = BN >= 32 ? 32 : 16;
+      constexpr int CH = BN >= 64 ? 32 : 16;
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t r[CH];
@@ -311,30 +381,32 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&scale_empty[ss]);
       if (warp == 8 && lane == 0 && i < 8) trace_stamp(args, 120 + i);
     }
+    if (iters == 0) griddep_wait();          // (an empty split-K rank still orders its stores behind the preceding kernel)
     if (warp == 8 && lane == 0) trace_stamp(args, 2);
     constexpr float kInv = 1.0f / 256.0f;   // exact: removes the 16 * 16 operand factor
-    griddep_wait();                          // the output buffer may still be read by the preceding kernel
 
     if constexpr (kEpi == EPI_O16) {
       // ---------------------------------------------------------- split-K: rank d reduces + stores token columns
-      // [d * CPR, (d + 1) * CPR).  Partials are PUSHED (no DSMEM read latency on the critical path), published by one
-      // cluster barrier and summed in rank order 0..kSplit-1, so the result does not depend on arrival order.
+      // [d * CPR, (d + 1) * CPR).  Partials travel as st.async messages that also complete transaction bytes on the
+      // owner's mbarrier: no cluster barrier, and the owner sums in rank order 0..kSplit-1 (deterministic).
       if constexpr (kSplit > 1) {
         cluster_wait();                      // pairs with the setup arrive: every CTA of the cluster is running
+        const uint32_t red_local = smem_u32(smem + C::OFF_RED), bar_local = smem_u32(red_full);
 #pragma unroll
         for (int d = 0; d < kSplit; ++d) {
           if (d != (int)krank) {
             const int slot_in_dst = (int)krank < d ? (int)krank : (int)krank - 1;
-            const uint32_t remote = mapa_shared(smem_u32(smem + C::OFF_RED), d) + slot_in_dst * C::RED_BYTES;
+            const uint32_t remote = mapa_shared(red_local, d) + slot_in_dst * C::RED_BYTES + row * (C::CPR * 4);
+            const uint32_t rbar = mapa_shared(bar_local, d);
 #pragma unroll
-            for (int c = 0; c < C::CPR; ++c) st_dsmem_f32(remote + (c * C::BM + row) * 4, acc[d * C::CPR + c]);
+            for (int c = 0; c < C::CPR; c += 4)
+              st_async_v4(remote + c * 4, acc[d * C::CPR + c], acc[d * C::CPR + c + 1], acc[d * C::CPR + c + 2],
+                          acc[d * C::CPR + c + 3], rbar);
           }
         }
-        cluster_arrive(); cluster_wait();
+        mbar_wait(red_full, 0);
         const float* red = reinterpret_cast<const float*>(smem + C::OFF_RED);
 #pragma unroll
         for (int d = 0; d < kSplit; ++d) {
@@ -344,7 +416,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
               float s = 0.f;
 #pragma unroll
               for (int rk = 0; rk < kSplit; ++rk) {
-                const float v = rk == d ? acc[d * C::CPR + c] : red[(rk < d ? rk : rk - 1) * (C::RED_BYTES / 4) + c * C::BM + row];
+                const float v = rk == d ? acc[d * C::CPR + c] : red[(rk < d ? rk : rk - 1) * (C::RED_BYTES / 4) + row * C::CPR + c];
                 s = rk == 0 ? v : s + v;
               }
               acc[d * C::CPR + c] = s;
@@ -396,10 +468,9 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   }
 
   // ---------------------------------------------------------------- teardown
-  if constexpr (kSplit > 1) {
-    if (warp < 8) { cluster_wait(); cluster_arrive(); cluster_wait(); }   // setup phase, then the epilogue's publish phase
-    // no CTA may exit while a peer can still push into its shared memory: the publish barrier above is that guarantee
-  }
+  // split-K: this CTA's shared memory is a target only until red_full completed (the epilogue waited for it), so no
+  // closing cluster barrier is needed; every thread still pairs its setup arrive with one wait.
+  if constexpr (kSplit > 1) { if (warp < 8) cluster_wait(); }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);

@@ -39,6 +39,8 @@ struct GemmArgs {
   int M, N, G;                   // G = number of INT4 groups = K/128 - 1
   int lda_scale;                 // S(M)
   unsigned long long* trace;     // optional device buffer [ctas][128] of clock64 stamps (atom_gemm_set_trace), else null
+  const uint8_t* a4;             // packed INT4 activations [M][(K-128)/2] and their INT8 keeper [M][128]: the decode kernel
+  const int8_t* a8;              //   reads the (tiny) token operand straight from global memory instead of through TMA
   int pdl;                       // launched with programmatic stream serialization: weights may be fetched before the
                                  // preceding kernel has finished, everything that reads activations waits (griddepcontrol)
 };

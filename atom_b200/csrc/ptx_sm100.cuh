@@ -182,4 +182,17 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   return v;
 }
 
+// L2-coherent loads (bypass L1) for data written by the PRECEDING kernel: under programmatic dependent launch this
+// kernel's CTAs share an SM (and its L1) with CTAs that were running before that data was produced
+__device__ __forceinline__ uint4 ld_cg_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 }  // namespace atom
