@@ -19,6 +19,7 @@
 #include "../../include/atom_b200.h"
 #include "gemm_i4_sm100.cuh"
 #include "gemm_i4_skinny_sm100.cuh"
+#include "gemm_i4_tall_sm100.cuh"
 #include "kv_kernels.cuh"
 #include "quant_kernels.cuh"
 
@@ -159,6 +160,33 @@ int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, u
   return ATOM_OK;
 }
 
+// The same byte matrix viewed as [rows/4][2][2][inner] with the two middle dimensions swapped: a box of `box_rows` rows
+// lands in shared memory in the order 4q+0, 4q+2, 4q+1, 4q+3 (gemm_i4_tall_sm100.cuh: neighbouring accumulator columns
+// then belong to different channel pairs).  rows % 4 == 0; rows beyond the matrix read as zero.
+int make_map_quadswap(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch, uint32_t box_inner,
+                      uint32_t box_rows, int swizzle) {
+  MapKey key{ptr, inner, rows, pitch, box_inner, box_rows, (uint32_t)swizzle | 0x100u};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return ATOM_OK; }
+  }
+  EncodeFn fn = encode_fn();
+  if (!fn) return fail(ATOM_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[4] = {inner, 2, 2, (rows + 3) / 4};
+  cuuint64_t strides[3] = {2 * pitch, pitch, 4 * pitch};
+  cuuint32_t box[4] = {box_inner, 2, 2, box_rows / 4};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ATOM_E_CUDA, "cuTensorMapEncodeTiled (4-D) failed with CUresult %d", (int)r);
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, *out);
+  return ATOM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM launch
 struct GemmOperands {
   const void *a, *b, *ak, *bk;
@@ -246,6 +274,37 @@ int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream
   return ATOM_OK;
 }
 
+// Prefill-shape kernel (gemm_i4_tall_sm100.cuh): biased accumulators, packed FP32 epilogue, TMA-permuted weight rows.
+template <bool kO4>
+int launch_tall(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
+  using C = atom::TallCfg<kO4>;
+  auto kern = atom::gemm_i4_tall_kernel<kO4>;
+  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (tall)");
+  if (rc) return rc;
+  const uint64_t kp = (uint64_t)(op.K - 128) / 2;
+  CUtensorMap tp4, tq4, tp8, tq8;
+  if ((rc = make_map(&tp4, op.a, kp, op.M, kp, 64, C::BM, 0))) return rc;
+  if ((rc = make_map_quadswap(&tq4, op.b, kp, op.N, kp, 64, C::BN, 0))) return rc;
+  if ((rc = make_map(&tp8, op.ak, 128, op.M, 128, 128, C::BM, 1))) return rc;
+  if ((rc = make_map_quadswap(&tq8, op.bk, 128, op.N, 128, 128, C::BN, 1))) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((op.N + C::BN - 1) / C::BN), (unsigned)((op.M + C::BM - 1) / C::BM), 1);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (gemm_pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tp4, tq4, tp8, tq8, args);
+  if (e != cudaSuccess) return fail(ATOM_E_CUDA, "gemm_i4 (tall) launch: %s", cudaGetErrorString(e));
+  return ATOM_OK;
+}
+
 template <bool kO4>
 int skinny_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   constexpr int kEpi = kO4 ? atom::EPI_O4 : atom::EPI_O16;
@@ -281,7 +340,8 @@ template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
   // <swap, BN, groups per pipeline stage, packed stages, K split, o4, converter warps, epilogue warpgroups>
-  if (!skinny) return launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream);
+  if (!skinny) return (flags & ATOM_GEMM_LEGACY_TALL) ? launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream)
+                                                      : launch_tall<kO4>(op, args, stream);
   if (op.M <= 64 && !(flags & ATOM_GEMM_LEGACY_SKINNY)) return skinny_dispatch<kO4>(op, args, flags, stream);
   // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not
   // cover the machine (the kernel is HBM-bound on the weights: more CTAs = more bytes in flight)

@@ -39,10 +39,13 @@ struct SkinnyCfg {
   static constexpr int BM = 128;                       // weight rows per tile = TMEM lanes
   static constexpr bool ONE_PER_SM = BN == 64;         // 64 accumulators per thread need > 80 registers
   static constexpr int TMEM_COLS = ONE_PER_SM ? 512 : 256;
-  static constexpr int A_RING = ONE_PER_SM ? 8 : 6;    // tensor-memory operand slots, 32 columns (one group) each
-  static constexpr int ACC = ONE_PER_SM ? 4 : 64 / BN; // accumulator slots of BN columns
-  static constexpr int NB = A_RING;                    // "group's MMAs completed" barriers (>= ACC)
-  static constexpr int A_COL0 = 0, ACC_COL0 = A_RING * 32;
+  // The unit of every hand-off (converter -> MMA -> epilogue) is a PAIR of quantisation groups: a wait on an mbarrier
+  // costs ~100 cycles even when the phase has completed and a tcgen05.commit ~200 cycles of the single issuing thread,
+  // against 32 tensor cycles for one group at 16 tokens (r02_gemm_skinny_v3_pipeline_trace.jsonl: 760 cycles per group
+  // in the MMA thread when every hand-off covered one group).
+  static constexpr int A_PAIRS = ONE_PER_SM ? 4 : (BN == 16 ? 3 : 2);   // tensor-memory operand slots (2 groups = 64 columns each)
+  static constexpr int ACC_PAIRS = 2;                  // accumulator slots (2 groups = 2 * BN columns each)
+  static constexpr int A_COL0 = 0, ACC_COL0 = A_PAIRS * 64;
   static constexpr int PACK = ONE_PER_SM ? 8 : (BN == 16 ? 6 : 5);   // packed weight ring depth (groups)
   static constexpr int QB = 4, QS = 2 * QB;            // token tiles: groups per hand-off, expanded slots
   static constexpr int SC = BN == 16 ? 32 : 16;        // groups per staged scale chunk
@@ -60,14 +63,15 @@ struct SkinnyCfg {
   static constexpr int OFF_RED = OFF_SA + SC * BN * 2;
   static constexpr int OFF_XCH = OFF_RED + (kSplit > 1 ? (kSplit - 1) * RED_BYTES : 0);   // o4: per-warp |v| min/max
   static constexpr int OFF_BAR = OFF_XCH + (kEpi == EPI_O4 ? 8 * BN * 4 : 0);
-  static constexpr int NUM_BARS = 2 * PACK + A_RING + 2 + NB + ACC + 3;
+  static constexpr int NUM_BARS = 2 * PACK + 2 * A_PAIRS + 4 + ACC_PAIRS + 3;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
   static constexpr int CTAS_PER_SM = ONE_PER_SM ? 1 : 2;
   static_assert(BN == 16 || BN == 32 || BN == 64, "token tile");
   static_assert(BN % kSplit == 0 && CPR >= 4, "every split-K rank owns at least 4 token columns");
   static_assert(kEpi == EPI_O16 || kSplit == 1, "the INT4-output epilogue quantises un-split FP32 sums");
-  static_assert(A_RING * 32 + ACC * BN <= TMEM_COLS, "tensor memory budget");
+  static_assert(A_PAIRS * 64 + ACC_PAIRS * 2 * BN <= TMEM_COLS, "tensor memory budget");
+  static_assert(A_PAIRS >= ACC_PAIRS, "mma_done is indexed by operand slot");
   static_assert(ONE_PER_SM ? SMEM_BYTES <= 227 * 1024 : SMEM_BYTES <= 113 * 1024, "shared memory budget (two CTAs per SM)");
 };
 
@@ -110,11 +114,12 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* pack_full = bars;                           // TMA landed a group's packed weight tile            (1 + tx)
   uint64_t* pack_empty = pack_full + C::PACK;           // the converter warps have read it                   (4)
-  uint64_t* a_full = pack_empty + C::PACK;              // tensor-memory operand slot written                 (4)
-  uint64_t* qx_full = a_full + C::A_RING;               // a batch of QB expanded token tiles is in place     (2)
-  uint64_t* mma_done = qx_full + 2;                     // the group's MMAs completed (tcgen05.commit)        (1)
-  uint64_t* acc_empty = mma_done + C::NB;               // epilogue has read the accumulator slot             (4)
-  uint64_t* keep_full = acc_empty + C::ACC;             // INT8 keeper weights landed                         (1 + tx)
+  uint64_t* a_full = pack_empty + C::PACK;              // tensor-memory operand slot (a PAIR of groups) written (4)
+  uint64_t* mma_done = a_full + C::A_PAIRS;             // the pair's MMAs completed (tcgen05.commit)         (1)
+  uint64_t* qx_full = mma_done + C::A_PAIRS;            // a batch of QB expanded token tiles is in place     (2)
+  uint64_t* q_empty = qx_full + 2;                      // ... and has been consumed (tcgen05.commit)         (1)
+  uint64_t* acc_empty = q_empty + 2;                    // epilogue has read the accumulator pair             (4)
+  uint64_t* keep_full = acc_empty + C::ACC_PAIRS;       // INT8 keeper weights landed                         (1 + tx)
   uint64_t* kq_full = keep_full + 1;                    // INT8 keeper tokens copied                          (2)
   uint64_t* red_full = kq_full + 1;                     // split-K: every peer's partial has arrived          (1 + tx)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM_PTR);
@@ -134,6 +139,9 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   }
   const int iters = g_end - g_begin;                                  // groups of this CTA, the keeper (if any) last
   const int n4 = max(0, min(g_end, args.G) - g_begin);                // ... of which INT4
+  const bool has_keeper = n4 < iters;
+  const int np4 = (n4 + 1) >> 1;                                      // INT4 units (pairs; the last may be single)
+  const int nu = np4 + (has_keeper ? 1 : 0);                          // units: INT4 pairs, then the keeper on its own
   if (threadIdx.x == 0) { griddep_launch_dependents(); trace_stamp(args, 0); }
 
   // ---------------------------------------------------------------- setup
@@ -147,19 +155,18 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     for (int i = 0; i < first; ++i) {
       mbar_arrive_expect_tx(&pack_full[i], C::PACK_P);
       tma_load_2d(smem + C::OFF_PACK_P + i * C::PACK_P, &tm_p4, &pack_full[i], (g_begin + i) * 64, n0);
-      if (i < 16) trace_stamp(args, 8 + i);
+      if (i < 8) trace_stamp(args, 8 + i);
     }
-    if (n4 < iters) {                                                  // this rank owns the keeper group
+    if (has_keeper) {
       tma_prefetch_desc(&tm_p8);
       mbar_arrive_expect_tx(keep_full, C::BM * 128);
       tma_load_2d(smem + C::OFF_KEEP_P, &tm_p8, keep_full, 0, n0);
     }
   } else if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_empty[i], 4);
-    for (int i = 0; i < C::A_RING; ++i) mbar_init(&a_full[i], 4);
-    mbar_init(&qx_full[0], 2); mbar_init(&qx_full[1], 2);
-    for (int i = 0; i < C::NB; ++i) mbar_init(&mma_done[i], 1);
-    for (int i = 0; i < C::ACC; ++i) mbar_init(&acc_empty[i], 4);
+    for (int i = 0; i < C::A_PAIRS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&mma_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&qx_full[i], 2); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < C::ACC_PAIRS; ++i) mbar_init(&acc_empty[i], 4);
     mbar_init(kq_full, 2);
     mbar_init(red_full, 1);
     fence_barrier_init();
@@ -182,38 +189,44 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
         mbar_wait(&pack_empty[ps], ((i / C::PACK) & 1) ^ 1);
         mbar_arrive_expect_tx(&pack_full[ps], C::PACK_P);
         tma_load_2d(smem + C::OFF_PACK_P + ps * C::PACK_P, &tm_p4, &pack_full[ps], (g_begin + i) * 64, n0);
-        if (i < 16) trace_stamp(args, 8 + i);
+        if (i < 8) trace_stamp(args, 8 + i);
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
+    // ============================================================ MMA issuer (one thread), one commit per pair
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_i8(C::BM, BN);
-      for (int i = 0; i < iters; ++i) {
-        const int as = i % C::ACC;
-        if (i >= C::ACC) mbar_wait(&acc_empty[as], ((i / C::ACC) - 1) & 1);
-        const uint32_t d_tmem = tmem_base + C::ACC_COL0 + as * BN;
-        if (i < n4) {
-          const int ar = i % C::A_RING, b = i / C::QB;
-          if (i % C::QB == 0) mbar_wait(&qx_full[b & 1], (b >> 1) & 1);
-          mbar_wait(&a_full[ar], (i / C::A_RING) & 1);
+      for (int u = 0; u < nu; ++u) {
+        const int as = u % C::ACC_PAIRS;
+        if (u >= C::ACC_PAIRS) mbar_wait(&acc_empty[as], ((u / C::ACC_PAIRS) - 1) & 1);
+        const uint32_t d0 = tmem_base + C::ACC_COL0 + as * 2 * BN;
+        if (u < np4) {
+          const int ar = u % C::A_PAIRS, ng = min(2, n4 - 2 * u), b = u >> 1;     // QB = 4 groups = 2 pairs per batch
+          if ((u & 1) == 0) mbar_wait(&qx_full[b & 1], (b >> 1) & 1);
+          mbar_wait(&a_full[ar], (u / C::A_PAIRS) & 1);
           tc_fence_after();
-          if (i < 16) trace_stamp(args, 88 + i);
-          const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + (i % C::QS) * C::EXP_Q));
+          if (u < 8) trace_stamp(args, 88 + u);
+          for (int j = 0; j < ng; ++j) {
+            const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + ((2 * u + j) % C::QS) * C::EXP_Q));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)        // 4 x K=32: 8 tensor-memory columns of A, 32 B of each token row
-            umma_i8_ts(d_tmem, tmem_base + C::A_COL0 + ar * 32 + k * 8, dq + (uint64_t)(k * 2), idesc, k > 0);
+            for (int k = 0; k < 4; ++k)      // 4 x K=32: 8 tensor-memory columns of A, 32 B of each token row
+              umma_i8_ts(d0 + j * BN, tmem_base + C::A_COL0 + ar * 64 + j * 32 + k * 8, dq + (uint64_t)(k * 2), idesc, k > 0);
+          }
+          if (u < 8) trace_stamp(args, 16 + u);
+          if ((u & 1) == 1 || u == np4 - 1) umma_commit(&q_empty[b & 1]);    // the batch's token tiles are consumed
         } else {
           mbar_wait(keep_full, 0);
           mbar_wait(kq_full, 0);
           tc_fence_after();
-          if (i < 16) trace_stamp(args, 88 + i);
+          if (u < 8) trace_stamp(args, 88 + u);
           const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + C::OFF_KEEP_P));
           const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_KEEP_Q));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_i8(d_tmem, dp + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k > 0);
+          for (int k = 0; k < 4; ++k) umma_i8(d0, dp + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k > 0);
+          if (u < 8) trace_stamp(args, 16 + u);
         }
-        umma_commit(&mma_done[i % C::NB]);   // accumulators ready AND operand slots reusable
+        umma_commit(&mma_done[u % C::A_PAIRS]);   // accumulators ready AND operand slot reusable
+        if (u < 8) trace_stamp(args, 32 + u);
       }
     }
   } else if (warp == 2 || warp == 3) {
@@ -225,50 +238,39 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     if (tq == 0) trace_stamp(args, 6);
     const int nbatch = (n4 + C::QB - 1) / C::QB;
     for (int b = 0; b < nbatch; ++b) {
-      if (b >= 2) { const int gl = (b - 1) * C::QB - 1; mbar_wait(&mma_done[gl % C::NB], (gl / C::NB) & 1); }   // slots free
+      if (b >= 2) mbar_wait(&q_empty[b & 1], ((b >> 1) - 1) & 1);
       const int ng = min(C::QB, n4 - b * C::QB), chunks = ng * BN * 4;
       for (int c0 = 0; c0 < chunks; c0 += 256) {
         uint4 w[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = c0 + u * 64 + tq;
-          w[u] = make_uint4(0, 0, 0, 0);
+        for (int x = 0; x < 4; ++x) {
+          const int c = c0 + x * 64 + tq;
+          w[x] = make_uint4(0, 0, 0, 0);
           if (c < chunks) {
             const int grp = c / (BN * 4), r = (c % (BN * 4)) >> 2, j = c & 3;
             if (m0 + r < args.M)
-              w[u] = ld_cg_v4(args.a4 + (size_t)(m0 + r) * kp + (size_t)(g_begin + b * C::QB + grp) * 64 + j * 16);
+              w[x] = ld_cg_v4(args.a4 + (size_t)(m0 + r) * kp + (size_t)(g_begin + b * C::QB + grp) * 64 + j * 16);
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = c0 + u * 64 + tq;
+        for (int x = 0; x < 4; ++x) {
+          const int c = c0 + x * 64 + tq;
           if (c < chunks) {
             const int grp = c / (BN * 4), r = (c % (BN * 4)) >> 2, j = c & 3;
             uint4 lo, hi;
-            expand_chunk(w[u], lo, hi);
+            expand_chunk(w[x], lo, hi);
             uint8_t* row = smem + C::OFF_EXP_Q + ((b * C::QB + grp) % C::QS) * C::EXP_Q + (r >> 3) * 1024 + (r & 7) * 128;
             *reinterpret_cast<uint4*>(row + (((2 * j) ^ (r & 7)) << 4)) = lo;
             *reinterpret_cast<uint4*>(row + (((2 * j + 1) ^ (r & 7)) << 4)) = hi;
           }
         }
       }
-      if (b == 0 && n4 < iters) {                          // keeper tokens: plain copy into the SWIZZLE_128B layout
-        for (int c = tq; c < BN * 8; c += 64) {
-          const int r = c >> 3, j = c & 7;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (m0 + r < args.M) v = ld_cg_v4(args.a8 + (size_t)(m0 + r) * 128 + j * 16);
-          *reinterpret_cast<uint4*>(smem + C::OFF_KEEP_Q + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = v;
-        }
-      }
       fence_proxy_async_smem();            // generic-proxy stores -> visible to the MMA's operand fetch
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&qx_full[b & 1]);
-        if (b == 0 && n4 < iters) mbar_arrive(kq_full);
-      }
+      if (lane == 0) mbar_arrive(&qx_full[b & 1]);
       if (tq == 0 && b == 0) trace_stamp(args, 5);
     }
-    if (nbatch == 0 && n4 < iters) {                       // keeper-only rank
+    if (has_keeper) {                                      // keeper tokens: plain copy into the SWIZZLE_128B layout
       for (int c = tq; c < BN * 8; c += 64) {
         const int r = c >> 3, j = c & 7;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -283,35 +285,38 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     // ============================================================ weight converters: thread = weight row
     const int wq = warp & 3, row = wq * 32 + lane, t = (warp - 4) * 32 + lane;
     const int xr = (row >> 1) & 3;                       // SWIZZLE_64B: 16-B chunk index ^= address bits [7,9)
-    for (int i = 0; i < n4; ++i) {
-      const int ps = i % C::PACK, ar = i % C::A_RING;
-      if (i >= C::A_RING) mbar_wait(&mma_done[ar], ((i / C::A_RING) - 1) & 1);     // NB == A_RING
-      if (t == 0 && i < 16) trace_stamp(args, 24 + i);
-      mbar_wait(&pack_full[ps], (i / C::PACK) & 1);
-      if (t == 0 && i < 16) trace_stamp(args, 40 + i);
-      const uint8_t* prow = smem + C::OFF_PACK_P + ps * C::PACK_P + row * 64;
-      uint4 w[4];
+    for (int u = 0; u < np4; ++u) {
+      const int ar = u % C::A_PAIRS, ng = min(2, n4 - 2 * u);
+      if (u >= C::A_PAIRS) mbar_wait(&mma_done[ar], ((u / C::A_PAIRS) - 1) & 1);
+      if (t == 0 && u < 8) trace_stamp(args, 24 + u);
+      for (int j = 0; j < ng; ++j) {
+        const int i = 2 * u + j, ps = i % C::PACK;
+        mbar_wait(&pack_full[ps], (i / C::PACK) & 1);
+        if (t == 0 && u < 8 && j == 0) trace_stamp(args, 40 + u);
+        const uint8_t* prow = smem + C::OFF_PACK_P + ps * C::PACK_P + row * 64;
+        uint4 w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const uint4*>(prow + ((j ^ xr) << 4));
-      // chunk j (32 consecutive K) -> columns 8j..8j+7: four "even element" words, then four "odd element" words
-      // (the token tiles use the same K permutation, so dot products are unchanged)
-      uint32_t r[32];
+        for (int x = 0; x < 4; ++x) w[x] = *reinterpret_cast<const uint4*>(prow + ((x ^ xr) << 4));
+        // chunk x (32 consecutive K) -> columns 8x..8x+7: four "even element" words, then four "odd element" words
+        // (the token tiles use the same K permutation, so dot products are unchanged)
+        uint32_t r[32];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 lo, hi;
-        expand_chunk(w[j], lo, hi);
-        r[8 * j + 0] = lo.x; r[8 * j + 1] = lo.y; r[8 * j + 2] = lo.z; r[8 * j + 3] = lo.w;
-        r[8 * j + 4] = hi.x; r[8 * j + 5] = hi.y; r[8 * j + 6] = hi.z; r[8 * j + 7] = hi.w;
+        for (int x = 0; x < 4; ++x) {
+          uint4 lo, hi;
+          expand_chunk(w[x], lo, hi);
+          r[8 * x + 0] = lo.x; r[8 * x + 1] = lo.y; r[8 * x + 2] = lo.z; r[8 * x + 3] = lo.w;
+          r[8 * x + 4] = hi.x; r[8 * x + 5] = hi.y; r[8 * x + 6] = hi.z; r[8 * x + 7] = hi.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pack_empty[ps]);     // the packed tile is in registers: the slot can be refilled
+        tmem_st_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::A_COL0 + ar * 64 + j * 32), r);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&pack_empty[ps]);       // the packed tile is in registers: the slot can be refilled
-      tmem_st_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::A_COL0 + ar * 32), r);
       tmem_st_wait();
-      if (t == 0 && i < 16) trace_stamp(args, 56 + i);
+      if (t == 0 && u < 8) trace_stamp(args, 56 + u);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[ar]);
-      if (t == 0 && i < 16) trace_stamp(args, 72 + i);
+      if (t == 0 && u < 8) trace_stamp(args, 72 + u);
     }
   } else if (warp >= 8) {
     // ============================================================ epilogue: thread = output channel (TMEM lane)
@@ -321,69 +326,75 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     for (int c = 0; c < BN; ++c) acc[c] = 0.f;
     __half* sb_s = reinterpret_cast<__half*>(smem + C::OFF_SB);
     uint32_t* sa_s = reinterpret_cast<uint32_t*>(smem + C::OFF_SA);
+    int staged_from = 0, staged_to = 0;      // groups [staged_from, staged_to) have their scale rows in shared memory
 
-    for (int i = 0; i < iters; ++i) {
-      if (i % C::SC == 0) {
-        // ---- stage the scale rows of groups [i, i + SC): weight scales first (no dependency), then activation scales
-        const int ng = min(C::SC, iters - i);
-        if (i > 0) asm volatile("bar.sync 2, 128;" ::: "memory");        // everyone is done with the previous chunk
-        for (int c = te; c < ng * 16; c += 128) {
-          const int gi = c >> 4, part = c & 15, g = g_begin + i + gi;
+    for (int u = 0; u < nu; ++u) {
+      const int i0 = u < np4 ? 2 * u : n4, ng = u < np4 ? min(2, n4 - 2 * u) : 1;
+      if (i0 + ng > staged_to) {
+        // ---- stage the scale rows of groups [i0, i0 + SC): weight scales first (no dependency), then activation scales
+        const int cnt = min(C::SC, iters - i0);
+        if (u > 0) asm volatile("bar.sync 2, 128;" ::: "memory");        // everyone is done with the previous chunk
+        for (int c = te; c < cnt * 16; c += 128) {
+          const int gi = c >> 4, part = c & 15, g = g_begin + i0 + gi;
           const __half* bs_row = (g == args.G) ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
           uint4 v = make_uint4(0, 0, 0, 0);
           if (n0 + 8 * part < args.N) v = ld_nc_v4(bs_row + n0 + 8 * part);
           reinterpret_cast<uint4*>(sb_s)[c] = v;
         }
-        if (i == 0) griddep_wait();
-        for (int c = te; c < ng * (BN / 2); c += 128) {
-          const int gi = c / (BN / 2), w = c % (BN / 2), blk = w >> 3, r = w & 7, g = g_begin + i + gi;
+        if (u == 0) griddep_wait();
+        for (int c = te; c < cnt * (BN / 2); c += 128) {
+          const int gi = c / (BN / 2), w = c % (BN / 2), blk = w >> 3, r = w & 7, g = g_begin + i0 + gi;
           const __half* as_row = (g == args.G) ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
           uint32_t v = 0;
           if (m0 + 16 * blk + r < args.M) v = ld_cg_u32(as_row + 64 * (m0 / 16 + blk) + 8 * r);
           sa_s[c] = v;
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (te == 0 && i == 0) trace_stamp(args, 7);
+        staged_from = i0; staged_to = i0 + cnt;
+        if (te == 0 && u == 0) trace_stamp(args, 7);
       }
-      const int as = i % C::ACC, si = i % C::SC;
-      const bool keeper = (g_begin + i == args.G);
-      const __half2 sm2 = reinterpret_cast<const __half2*>(sb_s + si * 128)[row >> 1];   // {sB[n & ~1], sB[n | 1]}
-      const __half2* snw = reinterpret_cast<const __half2*>(sa_s + si * (BN / 2));       // (sA[tok], sA[tok + 8]) words
-      mbar_wait(&mma_done[i % C::NB], (i / C::NB) & 1);
+      const int as = u % C::ACC_PAIRS;
+      mbar_wait(&mma_done[u % C::A_PAIRS], (u / C::A_PAIRS) & 1);
       tc_fence_after();
-      if (warp == 8 && lane == 0 && i < 16) trace_stamp(args, 104 + i);
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::ACC_COL0 + as * BN);
-      constexpr int CH = BN >= 64 ? 32 : 16;
+      if (warp == 8 && lane == 0 && u < 8) trace_stamp(args, 104 + u);
+      for (int j = 0; j < ng; ++j) {
+        const int si = i0 + j - staged_from;
+        const bool keeper = (g_begin + i0 + j == args.G);
+        const __half2 sm2 = reinterpret_cast<const __half2*>(sb_s + si * 128)[row >> 1];   // {sB[n & ~1], sB[n | 1]}
+        const __half2* snw = reinterpret_cast<const __half2*>(sa_s + si * (BN / 2));       // (sA[tok], sA[tok + 8]) words
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::ACC_COL0 + as * 2 * BN + j * BN);
+        constexpr int CH = BN >= 64 ? 32 : 16;
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += CH) {
-        uint32_t r[CH];
-        if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r); else tmem_ld_32x32b_x16(taddr + c0, r);
-        tmem_ld_wait();
-        if (c0 + CH == BN) {               // the group's accumulators are in registers: hand the slot back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
-        }
-        if (keeper) {                       // INT4 groups carry 16 * 16 = 256; lift the keeper to the same domain
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t r[CH];
+          if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r); else tmem_ld_32x32b_x16(taddr + c0, r);
+          tmem_ld_wait();
+          if (c0 + CH == BN && j == ng - 1) {     // the pair's accumulators are in registers: hand the slot back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+          }
+          if (keeper) {                       // INT4 groups carry 16 * 16 = 256; lift the keeper to the same domain
 #pragma unroll
-          for (int e = 0; e < CH; ++e) r[e] = (uint32_t)((int32_t)r[e] << 8);
-        }
-        // token c with c%16 < 8 pairs with sB[n & ~1], c%16 >= 8 with sB[n | 1] (the reference's column pairing,
-        // Dense_layer_gemm_i4_o16.cuh:417-431)
+            for (int e = 0; e < CH; ++e) r[e] = (uint32_t)((int32_t)r[e] << 8);
+          }
+          // token c with c%16 < 8 pairs with sB[n & ~1], c%16 >= 8 with sB[n | 1] (the reference's column pairing,
+          // Dense_layer_gemm_i4_o16.cuh:417-431)
 #pragma unroll
-        for (int q = 0; q < CH; q += 16) {
+          for (int q = 0; q < CH; q += 16) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const __half2 a2 = snw[((c0 + q) >> 4) * 8 + e];
-            const float2 rs = __half22float2(__hmul2(a2, sm2));
-            acc[c0 + q + e] = fmaf((float)(int32_t)r[q + e], rs.x, acc[c0 + q + e]);
-            acc[c0 + q + e + 8] = fmaf((float)(int32_t)r[q + e + 8], rs.y, acc[c0 + q + e + 8]);
+            for (int e = 0; e < 8; ++e) {
+              const __half2 a2 = snw[((c0 + q) >> 4) * 8 + e];
+              const float2 rs = __half22float2(__hmul2(a2, sm2));
+              acc[c0 + q + e] = fmaf((float)(int32_t)r[q + e], rs.x, acc[c0 + q + e]);
+              acc[c0 + q + e + 8] = fmaf((float)(int32_t)r[q + e + 8], rs.y, acc[c0 + q + e + 8]);
+            }
           }
         }
       }
-      if (warp == 8 && lane == 0 && i < 8) trace_stamp(args, 120 + i);
+      if (warp == 8 && lane == 0 && u < 8) trace_stamp(args, 120 + u);
     }
-    if (iters == 0) griddep_wait();          // (an empty split-K rank still orders its stores behind the preceding kernel)
+    if (nu == 0) griddep_wait();             // (an empty split-K rank still orders its stores behind the preceding kernel)
     if (warp == 8 && lane == 0) trace_stamp(args, 2);
     constexpr float kInv = 1.0f / 256.0f;   // exact: removes the 16 * 16 operand factor
 

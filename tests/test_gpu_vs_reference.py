@@ -56,7 +56,12 @@ def test_activate_equals_reference_kernel(m):
 
 
 @pytest.mark.parametrize("m,n,k,flags", [(16, 4096, 4096, 1), (7, 4096, 4096, 1), (128, 4096, 4096, 0), (1000, 4096, 4096, 0),
-                                         (4096, 4096, 4096, 0), (16, 11008, 4096, 1), (33, 4096, 11008, 1), (300, 4096, 11008, 0)])
+                                         (4096, 4096, 4096, 0), (16, 11008, 4096, 1), (33, 4096, 11008, 1), (300, 4096, 11008, 0),
+                                         # Llama-13B (config #4) and Llama-65B TP-8 (config #5) projection shapes, decode batch 32
+                                         (32, 5120, 5120, 1), (32, 13824, 5120, 1), (32, 5120, 13824, 1), (32, 1024, 8192, 1),
+                                         (32, 8192, 2816, 1), (32, 8192, 2688, 1), (64, 8192, 1024, 1),
+                                         # prefill: the 7B MLP up-projection and config #3's 16 x 2048 tokens
+                                         (4096, 11008, 4096, 0), (32768, 4096, 4096, 0)])
 def test_gemm_o16_equals_reference_kernel(m, n, k, flags):
     from atom_b200 import ops
     t = [T(x) for x in O.make_gemm_inputs(m, n, k, seed=m + n + k, pair_shared=(m % 2 == 0))]
@@ -74,7 +79,7 @@ def test_gemm_o16_splitk_within_one_ulp_of_reference_kernel():
     assert (ours != ref).float().mean().item() < 0.02
 
 
-@pytest.mark.parametrize("m,flags", [(16, 1), (100, 0), (1000, 0)])
+@pytest.mark.parametrize("m,flags", [(16, 1), (16, 0), (33, 0), (100, 0), (1000, 0)])      # flags 0 = the default dispatch (o4 never splits K)
 def test_gemm_o4_equals_reference_kernel(m, flags):
     from atom_b200 import ops
     t = [T(x) for x in O.make_gemm_inputs(m, 4096, 4096, seed=m)]

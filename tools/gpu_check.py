@@ -149,19 +149,11 @@ def gtiming(ms_list, n=4096, k=4096):
         elif m <= 128:
             variants["skinny"] = 4
         if m > 64:
-            variants["tall"] = 2
-            if os.environ.get("ATOM_EXPERIMENTAL") == "1":
-                variants["fp16path"] = 64      # experimental FP16-path prefill kernel (gemm_f16path_sm100.cuh)
+            variants["legacy_tall"] = 256
         launches = nrot if m <= 512 else 6
         for name, flags in variants.items():
             us = graph_time(lambda i: ops.dense_layer_gemm_i4_fp16(*sets[i % nrot], flags=flags), nrot, launches=launches)
             rec[name] = {"us": round(us, 2), "TOPS": round(ops_count / us * 1e-6, 1)}
-        if "fp16path" in variants:       # same kernel fed from weights expanded to FP16 once (prefill cache variant)
-            wx = [ops.expand_weights_f16(s_[1], s_[3], s_[5], s_[7]) for s_ in sets]
-            us = graph_time(lambda i: ops.dense_layer_gemm_i4_fp16_wx(sets[i % nrot][0], sets[i % nrot][2], sets[i % nrot][4],
-                                                                      sets[i % nrot][6], wx[i % nrot]), nrot, launches=launches)
-            rec["fp16path_wx"] = {"us": round(us, 2), "TOPS": round(ops_count / us * 1e-6, 1)}
-            del wx
         if R.available() and m in (16, 4096):
             us = graph_time(lambda i: R.gemm_i4_o16(*sets[i % nrot], d=outs[i % nrot], sync=0), nrot, launches=4, reps=5) \
                 if False else None   # the reference launches on the legacy stream: not capturable; use event timing
@@ -189,9 +181,12 @@ def trace(m, flags, n=4096, k=4096):
         r = b[cta]; t0 = r[0]
         rel = lambda x: None if x == 0 else int(x - t0)
         names = ["producer", "conv_slot", "conv_data", "conv_stored", "conv_arrived", "mma_woke", "acc_ready"]
-        d = {"setup": rel(r[1]), "epi_loop_done": rel(r[2]), "reduced": rel(r[3]), "end": rel(r[4])}
+        d = {"setup": rel(r[1]), "epi_loop_done": rel(r[2]), "reduced": rel(r[3]), "end": rel(r[4]),
+             "q_batch0_ready": rel(r[5]), "dependency_resolved": rel(r[6]), "scales_staged": rel(r[7])}
         for i, nm in enumerate(names):
-            d[nm] = [rel(x) for x in r[8 + 16 * i:8 + 16 * i + 10]]
+            d[nm] = [rel(x) for x in r[8 + 16 * i:8 + 16 * i + 8]]
+        d["mma_issued"] = [rel(x) for x in r[16:24]]          # decode kernel only (slots free there)
+        d["mma_committed"] = [rel(x) for x in r[32:40]]
         d["epi_done"] = [rel(x) for x in r[120:128]]
         out[f"cta{cta}"] = d
     print(json.dumps(out), flush=True)

@@ -27,7 +27,8 @@ for s in $STEPS; do case $s in
            timeout 300 python tools/gpu_check.py gtime 16 32 64 2> $OUT/sk_gtime.err | tee $OUT/sk_gtime.jsonl; tail -3 $OUT/sk_gtime.err
            ATOM_B200_GEMM_PDL=0 timeout 300 python tools/gpu_check.py gtime 16 2>> $OUT/sk_gtime.err | tee $OUT/sk_gtime_nopdl.jsonl
            timeout 300 python tools/gpu_check.py gshape 2>> $OUT/sk_gtime.err | tee $OUT/sk_gshape.jsonl
+           timeout 300 python tools/gpu_check.py gtime 128 256 1024 4096 2>> $OUT/sk_gtime.err | tee $OUT/tall_gtime.jsonl
            : > $OUT/sk_trace.jsonl
-           for cfg in "16 0" "16 1"; do timeout 120 python tools/gpu_check.py trace $cfg 2>&1 | tail -1 | tee -a $OUT/sk_trace.jsonl | cut -c1-2500; done ;;
+           for cfg in "16 0" "16 1" "4096 0" "4096 256"; do timeout 120 python tools/gpu_check.py trace $cfg 2>&1 | tail -1 | tee -a $OUT/sk_trace.jsonl | cut -c1-2500; done ;;
   *) echo "unknown step $s" ;;
 esac; done
