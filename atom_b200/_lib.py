@@ -18,6 +18,7 @@ _SIGNATURES = {
     "atom_scale_size": (_I, [_I]),
     "atom_reorder_fp16_i4": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "atom_rmsnorm_fp16_i4": (_I, [_P, _P, _F, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "atom_add_rmsnorm_fp16_i4": (_I, [_P, _P, _P, _P, _F, _P, _I, _I, _P, _P, _P, _P, _P]),
     "atom_activate_fp16_i4": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "atom_gemm_i4_o16": (_I, [_P] * 9 + [_I64, _I64, _I64, _U32, _P]),
     "atom_gemm_i4_o4": (_I, [_P] * 10 + [_I64, _I64, _I64, _U32, _P]),

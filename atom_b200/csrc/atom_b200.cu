@@ -85,7 +85,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): raise it once for each pair, under a lock
 // (the reference calls cudaFuncSetAttribute on every launch, GEMM.cuh:757).
 template <typename F>
-int ensure_dynamic_smem(F* func, int bytes, const char* what) {
+int ensure_dynamic_smem(F* func, int bytes, const char* what, bool max_carveout = false) {
   static std::mutex mu;
   static std::set<std::pair<const void*, int>> done;
   int dev = 0;
@@ -95,6 +95,10 @@ int ensure_dynamic_smem(F* func, int bytes, const char* what) {
   if (done.count(key)) return ATOM_OK;
   cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return fail(ATOM_E_CUDA, "%s: cudaFuncSetAttribute(smem=%d): %s", what, bytes, cudaGetErrorString(e));
+  if (max_carveout) {   // two ~100 KB CTAs per SM only fit when the SM's L1/shared split is at its shared-memory maximum
+    e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fail(ATOM_E_CUDA, "%s: cudaFuncSetAttribute(carveout): %s", what, cudaGetErrorString(e));
+  }
   done.insert(key);
   return ATOM_OK;
 }
@@ -248,7 +252,7 @@ template <int BN, int kSplit, int kEpi>
 int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
   using C = atom::SkinnyCfg<BN, kSplit, kEpi>;
   auto kern = atom::gemm_i4_skinny_kernel<BN, kSplit, kEpi>;
-  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (skinny)");
+  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (skinny)", true);
   if (rc) return rc;
   const uint64_t kp = (uint64_t)(op.K - 128) / 2;
   CUtensorMap tp4, tp8;       // weights only: the token operand is read with plain loads (no descriptor per activation buffer)
@@ -431,9 +435,24 @@ int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, cons
   ATOM_REQUIRE(hidden_dim <= 32768, "rmsnorm_fp16_i4: hidden_dim=%d > 32768 unsupported", hidden_dim);
   if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel, 32768 * 4 + 512, "rmsnorm_fp16_i4"))) return rc;   // row + weight (fp16) + reduction scratch
   return launch_k("rmsnorm_fp16_i4", atom::rmsnorm_quant_kernel, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 4 + 512,
-                  (cudaStream_t)stream, (const __half*)hidden, (const __half*)weight, eps, (const int16_t*)reorder_index, seq_len,
-                  hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales, (__half*)norm_scales,
-                  atom::scale_size(seq_len));
+                  (cudaStream_t)stream, (const __half*)hidden, (const __half*)nullptr, (__half*)nullptr, (const __half*)weight, eps,
+                  (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales,
+                  (__half*)norm_scales, atom::scale_size(seq_len));
+}
+
+int atom_add_rmsnorm_fp16_i4(const void* hidden, const void* residual, void* sum_out, const void* weight, float eps,
+                             const void* reorder_index, int seq_len, int hidden_dim, void* o_outliers, void* o_norms,
+                             void* outlier_scales, void* norm_scales, void* stream) {
+  int rc = quant_check("add_rmsnorm_fp16_i4", seq_len, hidden_dim, o_outliers, o_norms, outlier_scales, norm_scales);
+  if (rc) return rc;
+  ATOM_REQUIRE(hidden && residual && sum_out && weight && reorder_index && aligned16(hidden) && aligned16(residual) && aligned16(sum_out) &&
+               aligned16(weight), "add_rmsnorm_fp16_i4: null or misaligned input");
+  ATOM_REQUIRE(hidden_dim <= 32768, "add_rmsnorm_fp16_i4: hidden_dim=%d > 32768 unsupported", hidden_dim);
+  if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel, 32768 * 4 + 512, "add_rmsnorm_fp16_i4"))) return rc;
+  return launch_k("add_rmsnorm_fp16_i4", atom::rmsnorm_quant_kernel, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 4 + 512,
+                  (cudaStream_t)stream, (const __half*)hidden, (const __half*)residual, (__half*)sum_out, (const __half*)weight, eps,
+                  (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales,
+                  (__half*)norm_scales, atom::scale_size(seq_len));
 }
 
 int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, int hidden_dim, void* o_outliers, void* o_norms,

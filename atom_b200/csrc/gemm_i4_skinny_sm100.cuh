@@ -102,6 +102,19 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float
                ::"r"(remote_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar) : "memory");
 }
 
+// 16 token columns of one group: acc[c] = fmaf(float(c_int), float(hmul(sA[c], sB)), acc[c]).  Token c with c%16 < 8 pairs
+// with sB[n & ~1], c%16 >= 8 with sB[n | 1] (the reference's column pairing, Dense_layer_gemm_i4_o16.cuh:417-431).
+__device__ __forceinline__ void dequant16(float* acc, const uint32_t* r, const __half2* snw, __half2 sm2, bool keeper) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float2 rs = __half22float2(__hmul2(snw[e], sm2));
+    int32_t lo = (int32_t)r[e], hi = (int32_t)r[e + 8];
+    if (keeper) { lo <<= 8; hi <<= 8; }        // INT4 groups carry 16 * 16 = 256; lift the keeper to the same domain
+    acc[e] = fmaf((float)lo, rs.x, acc[e]);
+    acc[e + 8] = fmaf((float)hi, rs.y, acc[e + 8]);
+  }
+}
+
 template <int BN, int kSplit, int kEpi>
 __global__ void __launch_bounds__(SkinnyCfg<BN, kSplit, kEpi>::THREADS, SkinnyCfg<BN, kSplit, kEpi>::CTAS_PER_SM)
 gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 weights   (box 64 B x 128 rows, SWIZZLE_64B)
@@ -145,23 +158,27 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   if (threadIdx.x == 0) { griddep_launch_dependents(); trace_stamp(args, 0); }
 
   // ---------------------------------------------------------------- setup
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_p4);
-    for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_full[i], 1);
-    mbar_init(keep_full, 1);
-    fence_barrier_init();
-    // the weight stream starts before anything else exists: it depends on nothing
+  if (warp == 0) {
+    // the weight stream starts before anything else exists: it depends on nothing.  One ELECTED lane of the converged
+    // warp issues (uniform operands -> no per-lane broadcast loop around every TMA instruction)
     const int first = min(C::PACK, n4);
-    for (int i = 0; i < first; ++i) {
-      mbar_arrive_expect_tx(&pack_full[i], C::PACK_P);
-      tma_load_2d(smem + C::OFF_PACK_P + i * C::PACK_P, &tm_p4, &pack_full[i], (g_begin + i) * 64, n0);
-      if (i < 8) trace_stamp(args, 8 + i);
+    if (elect_one_sync()) {
+      tma_prefetch_desc(&tm_p4);
+      for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_full[i], 1);
+      mbar_init(keep_full, 1);
+      fence_barrier_init();
+      for (int i = 0; i < first; ++i) {
+        mbar_arrive_expect_tx(&pack_full[i], C::PACK_P);
+        tma_load_2d(smem + C::OFF_PACK_P + i * C::PACK_P, &tm_p4, &pack_full[i], (g_begin + i) * 64, n0);
+        if (i < 8) trace_stamp(args, 8 + i);
+      }
+      if (has_keeper) {
+        tma_prefetch_desc(&tm_p8);
+        mbar_arrive_expect_tx(keep_full, C::BM * 128);
+        tma_load_2d(smem + C::OFF_KEEP_P, &tm_p8, keep_full, 0, n0);
+      }
     }
-    if (has_keeper) {
-      tma_prefetch_desc(&tm_p8);
-      mbar_arrive_expect_tx(keep_full, C::BM * 128);
-      tma_load_2d(smem + C::OFF_KEEP_P, &tm_p8, keep_full, 0, n0);
-    }
+    __syncwarp();
   } else if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_empty[i], 4);
     for (int i = 0; i < C::A_PAIRS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&mma_done[i], 1); }
@@ -182,29 +199,31 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   if (threadIdx.x == 0) trace_stamp(args, 1);
 
   if (warp == 0) {
-    // ============================================================ weight TMA producer
-    if (lane == 0) {
-      for (int i = C::PACK; i < n4; ++i) {
-        const int ps = i % C::PACK;
-        mbar_wait(&pack_empty[ps], ((i / C::PACK) & 1) ^ 1);
+    // ============================================================ weight TMA producer (whole warp loops, one lane issues)
+    for (int i = C::PACK; i < n4; ++i) {
+      const int ps = i % C::PACK;
+      mbar_wait(&pack_empty[ps], ((i / C::PACK) & 1) ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&pack_full[ps], C::PACK_P);
         tma_load_2d(smem + C::OFF_PACK_P + ps * C::PACK_P, &tm_p4, &pack_full[ps], (g_begin + i) * 64, n0);
         if (i < 8) trace_stamp(args, 8 + i);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (one thread), one commit per pair
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_i8(C::BM, BN);
-      for (int u = 0; u < nu; ++u) {
-        const int as = u % C::ACC_PAIRS;
-        if (u >= C::ACC_PAIRS) mbar_wait(&acc_empty[as], ((u / C::ACC_PAIRS) - 1) & 1);
-        const uint32_t d0 = tmem_base + C::ACC_COL0 + as * 2 * BN;
-        if (u < np4) {
-          const int ar = u % C::A_PAIRS, ng = min(2, n4 - 2 * u), b = u >> 1;     // QB = 4 groups = 2 pairs per batch
-          if ((u & 1) == 0) mbar_wait(&qx_full[b & 1], (b >> 1) & 1);
-          mbar_wait(&a_full[ar], (u / C::A_PAIRS) & 1);
-          tc_fence_after();
+    // ============================================================ MMA issuer: the whole warp runs the loop (waits are
+    // uniform), ONE elected lane issues the tcgen05 instructions; one commit per pair
+    constexpr uint32_t idesc = umma_idesc_i8(C::BM, BN);
+    for (int u = 0; u < nu; ++u) {
+      const int as = u % C::ACC_PAIRS;
+      if (u >= C::ACC_PAIRS) mbar_wait(&acc_empty[as], ((u / C::ACC_PAIRS) - 1) & 1);
+      const uint32_t d0 = tmem_base + C::ACC_COL0 + as * 2 * BN;
+      if (u < np4) {
+        const int ar = u % C::A_PAIRS, ng = min(2, n4 - 2 * u), b = u >> 1;     // QB = 4 groups = 2 pairs per batch
+        if ((u & 1) == 0) mbar_wait(&qx_full[b & 1], (b >> 1) & 1);
+        mbar_wait(&a_full[ar], (u / C::A_PAIRS) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
           if (u < 8) trace_stamp(args, 88 + u);
           for (int j = 0; j < ng; ++j) {
             const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + ((2 * u + j) % C::QS) * C::EXP_Q));
@@ -214,20 +233,25 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
           }
           if (u < 8) trace_stamp(args, 16 + u);
           if ((u & 1) == 1 || u == np4 - 1) umma_commit(&q_empty[b & 1]);    // the batch's token tiles are consumed
-        } else {
-          mbar_wait(keep_full, 0);
-          mbar_wait(kq_full, 0);
-          tc_fence_after();
+          umma_commit(&mma_done[ar]);          // accumulators ready AND operand slot reusable
+          if (u < 8) trace_stamp(args, 32 + u);
+        }
+      } else {
+        mbar_wait(keep_full, 0);
+        mbar_wait(kq_full, 0);
+        tc_fence_after();
+        if (elect_one_sync()) {
           if (u < 8) trace_stamp(args, 88 + u);
           const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + C::OFF_KEEP_P));
           const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_KEEP_Q));
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_i8(d0, dp + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k > 0);
           if (u < 8) trace_stamp(args, 16 + u);
+          umma_commit(&mma_done[u % C::A_PAIRS]);
+          if (u < 8) trace_stamp(args, 32 + u);
         }
-        umma_commit(&mma_done[u % C::A_PAIRS]);   // accumulators ready AND operand slot reusable
-        if (u < 8) trace_stamp(args, 32 + u);
       }
+      __syncwarp();
     }
   } else if (warp == 2 || warp == 3) {
     // ============================================================ token tiles: global -> INT8 operand in smem
@@ -357,37 +381,43 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       mbar_wait(&mma_done[u % C::A_PAIRS], (u / C::A_PAIRS) & 1);
       tc_fence_after();
       if (warp == 8 && lane == 0 && u < 8) trace_stamp(args, 104 + u);
-      for (int j = 0; j < ng; ++j) {
-        const int si = i0 + j - staged_from;
-        const bool keeper = (g_begin + i0 + j == args.G);
-        const __half2 sm2 = reinterpret_cast<const __half2*>(sb_s + si * 128)[row >> 1];   // {sB[n & ~1], sB[n | 1]}
-        const __half2* snw = reinterpret_cast<const __half2*>(sa_s + si * (BN / 2));       // (sA[tok], sA[tok + 8]) words
-        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::ACC_COL0 + as * 2 * BN + j * BN);
-        constexpr int CH = BN >= 64 ? 32 : 16;
+      const uint32_t tpair = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::ACC_COL0 + as * 2 * BN);
+      if constexpr (BN == 16) {
+        // both groups of the pair with one tcgen05.ld (a single group: the upper half is stale and ignored)
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tpair, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);       // the pair's accumulators are in registers: hand the slot back
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += CH) {
-          uint32_t r[CH];
-          if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r); else tmem_ld_32x32b_x16(taddr + c0, r);
-          tmem_ld_wait();
-          if (c0 + CH == BN && j == ng - 1) {     // the pair's accumulators are in registers: hand the slot back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        for (int j = 0; j < 2; ++j) {
+          if (j < ng) {
+            const int si = i0 + j - staged_from;
+            const __half2 sm2 = reinterpret_cast<const __half2*>(sb_s + si * 128)[row >> 1];   // {sB[n & ~1], sB[n | 1]}
+            const __half2* snw = reinterpret_cast<const __half2*>(sa_s + si * (BN / 2));       // (sA[tok], sA[tok + 8]) words
+            dequant16(acc, r + 16 * j, snw, sm2, g_begin + i0 + j == args.G);
           }
-          if (keeper) {                       // INT4 groups carry 16 * 16 = 256; lift the keeper to the same domain
+        }
+      } else {
 #pragma unroll
-            for (int e = 0; e < CH; ++e) r[e] = (uint32_t)((int32_t)r[e] << 8);
-          }
-          // token c with c%16 < 8 pairs with sB[n & ~1], c%16 >= 8 with sB[n | 1] (the reference's column pairing,
-          // Dense_layer_gemm_i4_o16.cuh:417-431)
+        for (int j = 0; j < 2; ++j) {
+          if (j < ng) {
+            const int si = i0 + j - staged_from;
+            const bool keeper = (g_begin + i0 + j == args.G);
+            const __half2 sm2 = reinterpret_cast<const __half2*>(sb_s + si * 128)[row >> 1];
+            const __half2* snw = reinterpret_cast<const __half2*>(sa_s + si * (BN / 2));
 #pragma unroll
-          for (int q = 0; q < CH; q += 16) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const __half2 a2 = snw[((c0 + q) >> 4) * 8 + e];
-              const float2 rs = __half22float2(__hmul2(a2, sm2));
-              acc[c0 + q + e] = fmaf((float)(int32_t)r[q + e], rs.x, acc[c0 + q + e]);
-              acc[c0 + q + e + 8] = fmaf((float)(int32_t)r[q + e + 8], rs.y, acc[c0 + q + e + 8]);
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+              uint32_t r[16];
+              tmem_ld_32x32b_x16(tpair + j * BN + c0, r);
+              tmem_ld_wait();
+              if (c0 + 16 == BN && j == ng - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+              }
+              dequant16(acc + c0, r, snw + (c0 >> 4) * 8, sm2, keeper);
             }
           }
         }

@@ -129,11 +129,12 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
     if (s < 16 && (part & 2)) trace_stamp(args, 8 + s);
   };
   int s_w = 0;
-  if (warp == 0 && lane == 0) {
+  for (; s_w < C::PACK && s_w < nstages && stage_int4(s_w) > 0; ++s_w) {}     // stages whose weight tiles are issued up front
+  if (warp == 0 && elect_one_sync()) {       // an elected lane of the converged warp: uniform TMA operands
     tma_prefetch_desc(&tm_p4); tma_prefetch_desc(&tm_q4);
     for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_full[i], 1);
     fence_barrier_init();
-    for (; s_w < C::PACK && s_w < nstages && stage_int4(s_w) > 0; ++s_w) issue_stage(s_w, s_w, 1);   // weights first
+    for (int s = 0; s < s_w; ++s) issue_stage(s, s, 1);   // weights first
     tma_prefetch_desc(&tm_p8); tma_prefetch_desc(&tm_q8);
     for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_empty[i], 4);
     for (int i = 0; i < C::RING; ++i) { mbar_init(&exp_full[i], 4); mbar_init(&mma_done[i], 1); mbar_init(&tmem_empty[i], 4 * C::EPI_WGS); }
@@ -149,26 +150,26 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
 
   if (warp < 4) {
     if (warp == 0) {
-      // ============================================================ TMA producer
-      if (lane == 0) {
-        griddep_wait();                              // the token tiles are the preceding kernel's output
-        for (int s = 0; s < s_w; ++s) issue_stage(s, s, 2);
-        for (int s = s_w; s < nstages; ++s) {
-          if (stage_int4(s) == 0) break;             // a trailing keeper-only stage has nothing in the packed ring
-          const int ps = s % C::PACK;
-          mbar_wait(&pack_empty[ps], ((s / C::PACK) & 1) ^ 1);
-          issue_stage(s, ps, 3);
-        }
+      // ============================================================ TMA producer (warp loops, one elected lane issues)
+      griddep_wait();                              // the token tiles are the preceding kernel's output
+      if (elect_one_sync()) { for (int s = 0; s < s_w; ++s) issue_stage(s, s, 2); }
+      __syncwarp();
+      for (int s = s_w; s < nstages; ++s) {
+        if (stage_int4(s) == 0) break;             // a trailing keeper-only stage has nothing in the packed ring
+        const int ps = s % C::PACK;
+        mbar_wait(&pack_empty[ps], ((s / C::PACK) & 1) ^ 1);
+        if (elect_one_sync()) issue_stage(s, ps, 3);
+        __syncwarp();
       }
     } else if (warp == 1) {
-      // ============================================================ MMA issuer
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_i8(C::BM, BN);
-        for (int s = 0; s < nstages; ++s) {
-          const int es = s % C::RING;
-          mbar_wait(&tmem_empty[es], (s / C::RING) & 1);        // completion #0 is the initial arming of the slot
-          mbar_wait(&exp_full[es], (s / C::RING) & 1);
-          tc_fence_after();
+      // ============================================================ MMA issuer (warp loops, one elected lane issues)
+      constexpr uint32_t idesc = umma_idesc_i8(C::BM, BN);
+      for (int s = 0; s < nstages; ++s) {
+        const int es = s % C::RING;
+        mbar_wait(&tmem_empty[es], (s / C::RING) & 1);        // completion #0 is the initial arming of the slot
+        mbar_wait(&exp_full[es], (s / C::RING) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
           if (s < 16) trace_stamp(args, 88 + s);
           const int ng = stage_groups(s);
           for (int j = 0; j < ng; ++j) {
@@ -180,6 +181,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
           }
           umma_commit(&mma_done[es]);       // one commit per stage: epilogue may read, converter may refill
         }
+        __syncwarp();
       }
     } else if (warp == 3) {
       // ============================================================ scale loader.  Group slot (512 B):

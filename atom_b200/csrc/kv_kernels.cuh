@@ -67,8 +67,9 @@ append_kv_kernel(KvArgs kv, const uint8_t* __restrict__ k, const uint8_t* __rest
 // the bracket is advanced once per page by a constant rotation (FP32, kept in smem), e^{j t_lo theta} comes from a smem
 // table -- no transcendental per token (the reference evaluates __sincosf per element per token, decode.cuh:39-71).
 // The per-token arithmetic runs in packed half2: one LOP3 turns two nibbles into the halves (1024+n); HSUB2 makes them
-// exact; dequant, rotation and the q.k products are HFMA2 on nibble couples (j, j+4); scores, softmax statistics, the
-// page-level rescale and the output accumulators stay FP32 (V is accumulated in half2 only within one page).  An
+// exact; dequant and rotation are HFMA2 on nibble couples (j, j+4); the q.k products are accumulated in FP32 (FHFMA: FP16
+// inputs, exact product, FP32 sum); scores, softmax statistics, the page-level rescale and the output accumulators stay
+// FP32 (V is accumulated in half2 only within one page).  An
 // all-FP32 version of this kernel executed 75 M warp instructions per layer, 36 % of them nibble extraction/conversion.
 // Softmax is blocked per page; V dequant is folded: sum_t p_t (n s_t - z_t) = sum_t (p_t s_t) n - sum_t p_t z_t.
 constexpr int DEC_CONSUMERS = 4;
@@ -84,6 +85,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ __half2 nib2(uint32_t w, int q) {
   const uint32_t u = ((w >> (4 * q)) & 0x000F000Fu) | 0x64006400u;
   return __hsub2(*reinterpret_cast<const __half2*>(&u), __half2half2(__ushort_as_half(0x6400)));
+}
+
+// acc += a * b with FP16 inputs, an exact product and FP32 accumulation (one FHFMA; .H0 / .H1 operand selectors are free)
+__device__ __forceinline__ float fhfma(__half a, __half b, float acc) {
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)));
+  return acc;
 }
 
 template <int kMaxTpl>   // tokens per lane per page = P / 8 <= kMaxTpl
@@ -216,7 +223,7 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
         const __half2 kp = kpar[tl];
         const __half2 ks2 = __half2half2(__low2half(kp)), kz2 = __hneg2(__half2half2(__high2half(kp)));
         const uint2* trow = tabh + tl * 4 + c;
-        __half2 xa2 = __half2half2(__ushort_as_half(0)), xb2 = xa2;
+        float xa = 0.f, xb = 0.f;        // q.k is accumulated in FP32 (the reference's compute_qk is all-FP32, decode.cuh:92-124)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const uint32_t wl = (u < 4) ? k_lo.x : k_lo.y, wh = (u < 4) ? k_hi.x : k_hi.y;
@@ -225,11 +232,10 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
           const __half2 c2 = *reinterpret_cast<const __half2*>(&t.x), s2 = *reinterpret_cast<const __half2*>(&t.y);
           const __half2 rr = __hfma2(kre, c2, __hneg2(__hmul2(kim, s2)));      // Re(zk e^{j t_lo theta})
           const __half2 ri = __hfma2(kim, c2, __hmul2(kre, s2));
-          if (u & 1) { xb2 = __hfma2(qre2[u], rr, xb2); xb2 = __hfma2(qim2[u], ri, xb2); }
-          else       { xa2 = __hfma2(qre2[u], rr, xa2); xa2 = __hfma2(qim2[u], ri, xa2); }
+          xa = fhfma(__low2half(qre2[u]), __low2half(rr), xa);  xb = fhfma(__high2half(qre2[u]), __high2half(rr), xb);
+          xa = fhfma(__low2half(qim2[u]), __low2half(ri), xa);  xb = fhfma(__high2half(qim2[u]), __high2half(ri), xb);
         }
-        const float2 fa = __half22float2(xa2), fb = __half22float2(xb2);
-        float xs = (fa.x + fa.y) + (fb.x + fb.y);
+        float xs = xa + xb;
         xs += __shfl_xor_sync(0xffffffffu, xs, 1);
         xs += __shfl_xor_sync(0xffffffffu, xs, 2);
         x[i] = xs * kSmScale;

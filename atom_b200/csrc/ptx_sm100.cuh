@@ -62,6 +62,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp (elect.sync).  Instructions that take uniform-register operands (tcgen05.mma, commit,
+// TMA) should be issued under this predicate from warp-uniform control flow: inside `if (lane == 0)` the compiler must
+// assume per-lane operands and wraps every such instruction in a broadcast loop (4 R2UR + branch, ~70 cycles per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ proxies / fences
 // generic-proxy smem writes -> visible to the async proxy (TMA, tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -78,8 +78,11 @@ reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ i
 // s[t]+=s[t+64], s[t]+=s[t+32], then shfl_down 16..1 (RMSNorm.cuh:112-141).  The other 12 warps meanwhile stage
 // the norm weight; afterwards all 16 warps quantise groups (at decode sizes the kernel is one latency chain per row,
 // so the chain is kept short: 2 groups per warp at hidden 4096 instead of 8).
+// With `residual` != nullptr the row is x + residual (one FP16 RN add per element, exactly what `residual + hidden_states`
+// does in the reference's decoder layer, llama.py:266-292); the sum is also written to `sum_out` (the next residual).
 __global__ void __launch_bounds__(QUANT_THREADS)
-rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w, float eps, const int16_t* __restrict__ idx,
+rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ residual, __half* __restrict__ sum_out,
+                     const __half* __restrict__ w, float eps, const int16_t* __restrict__ idx,
                      int seq_len, int hidden, int8_t* __restrict__ s8out, uint8_t* __restrict__ s4out,
                      __half* __restrict__ s8scale, __half* __restrict__ s4scale, int scale_ldm, int pdl) {
   extern __shared__ __align__(16) uint8_t smem_q[];
@@ -99,7 +102,15 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
       reinterpret_cast<uint4*>(ws)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(w) + i);
   } else if ((ept & 7) == 0) {
     for (int i = 0; i < ept; i += 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + tid * ept + i);
+      uint4 u = *reinterpret_cast<const uint4*>(xr + tid * ept + i);
+      if (residual != nullptr) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(residual + (size_t)row * hidden + tid * ept + i);
+        __half2* hu = reinterpret_cast<__half2*>(&u);
+        const __half2* hr = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hu[j] = __hadd2(hu[j], hr[j]);
+        *reinterpret_cast<uint4*>(sum_out + (size_t)row * hidden + tid * ept + i) = u;
+      }
       *reinterpret_cast<uint4*>(xs + tid * ept + i) = u;
       const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -111,7 +122,11 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
     }
   } else {
     for (int i = 0; i < ept; ++i) {
-      const __half hv = xr[tid * ept + i];
+      __half hv = xr[tid * ept + i];
+      if (residual != nullptr) {
+        hv = __hadd(hv, residual[(size_t)row * hidden + tid * ept + i]);
+        sum_out[(size_t)row * hidden + tid * ept + i] = hv;
+      }
       xs[tid * ept + i] = hv;
       const float f = __half2float(hv);
       sumv = fmaf(f, f, sumv);

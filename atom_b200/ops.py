@@ -90,6 +90,27 @@ def rmsnorm_fp16_i4(hidden_states, weight, reorder_index, eps):
     return out
 
 
+def add_rmsnorm_fp16_i4(hidden_states, residual, weight, reorder_index, eps):
+    """EXTENSION: (residual + hidden_states) and rmsnorm_fp16_i4 of the sum in one launch.  Returns (sum, 4-tuple);
+    both bit-identical to `s = residual + hidden_states; rmsnorm_fp16_i4(s, ...)`."""
+    if isinstance(weight, torch.Tensor) and weight.dtype != torch.float16:
+        weight = weight.to(torch.float16)
+    _req_width("add_rmsnorm_fp16_i4", f16_hidden_states_2=hidden_states, f16_residual_2=residual, f16_weight_2=weight,
+               reorder_index_2=reorder_index)
+    _req_cuda(hidden_states, residual, weight, reorder_index)
+    if hidden_states.shape != residual.shape:
+        raise RuntimeError("add_rmsnorm_fp16_i4: hidden_states and residual must have the same shape")
+    bs, hidden_dim = hidden_states.shape
+    out = _quant_outputs(bs, hidden_dim, hidden_states.device)
+    s = torch.empty_like(hidden_states)
+    with torch.cuda.device(hidden_states.device):
+        _lib.check(_lib.lib().atom_add_rmsnorm_fp16_i4(hidden_states.data_ptr(), residual.data_ptr(), s.data_ptr(), weight.data_ptr(),
+                                                       float(eps), reorder_index.data_ptr(), bs, hidden_dim, out[0].data_ptr(),
+                                                       out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                                       _stream(hidden_states)), "add_rmsnorm_fp16_i4")
+    return s, out
+
+
 def activate_fp16_i4(a, b):
     """ops/__init__.py:141-157"""
     _req_width("activate_fp16_i4", f16_a_2=a, f16_b_2=b)

@@ -65,6 +65,13 @@ ATOM_API int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float 
                          int hidden_dim, void* o_outliers, void* o_norms, void* outlier_scales, void* norm_scales,
                          void* stream);
 
+/* EXTENSION (launch-count reduction): the residual add of the decoder layer
+ * (punica/models/llama.py:266-292, `hidden = residual + hidden`) folded into the following rmsnorm_fp16_i4:
+ * sum_out = hidden + residual (FP16 RN, bit-identical to the separate add), then exactly rmsnorm_fp16_i4(sum_out, ...). */
+ATOM_API int atom_add_rmsnorm_fp16_i4(const void* hidden, const void* residual, void* sum_out, const void* weight, float eps,
+                             const void* reorder_index, int seq_len, int hidden_dim, void* o_outliers, void* o_norms,
+                             void* outlier_scales, void* norm_scales, void* stream);
+
 /* replaces activate_fp16_i4 (punica_ops.cc:73-80 -> run_activate_fp16_i4<128,11008>, Activate.cuh:194-218) */
 ATOM_API int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, int hidden_dim, void* o_outliers, void* o_norms,
                           void* outlier_scales, void* norm_scales, void* stream);

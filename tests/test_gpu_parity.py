@@ -68,6 +68,24 @@ def test_rmsnorm_quant(m, h):
     _cmp_quant(ops.rmsnorm_fp16_i4(T(x), T(w), T(idx), 1e-5), O.rmsnorm_fp16_i4(x, w, idx, 1e-5), exact=False)
 
 
+@pytest.mark.parametrize("m,h", [(1, 4096), (16, 4096), (33, 5120), (7, 8192), (3, 384)])
+def test_add_rmsnorm_equals_add_then_rmsnorm(m, h):
+    """EXTENSION op (launch-count reduction): residual add folded into the norm+quantise kernel -- must be bit-identical to the
+    two-step form the reference's decoder layer executes (llama.py:266-292)."""
+    from atom_b200 import ops
+    rng = np.random.default_rng(m * 13 + h)
+    x, idx = _quant_inputs(rng, m, h)
+    res = (rng.standard_normal((m, h)) * 2).astype(np.float16)
+    w = (1 + 0.2 * rng.standard_normal(h)).astype(np.float16)
+    s, fused = ops.add_rmsnorm_fp16_i4(T(x), T(res), T(w), T(idx), 1e-5)
+    s_ref = T(res) + T(x)
+    two = ops.rmsnorm_fp16_i4(s_ref, T(w), T(idx), 1e-5)
+    assert torch.equal(s, s_ref)
+    assert torch.equal(fused[0], two[0]) and torch.equal(fused[1], two[1])
+    sel = torch.tensor([O.scale_index(r) + 2 * j for r in range(m) for j in range(4)], device="cuda:0")
+    assert torch.equal(fused[2][sel], two[2][sel]) and torch.equal(fused[3][:, sel], two[3][:, sel])
+
+
 @pytest.mark.parametrize("m,h", [(1, 11008), (7, 11008), (16, 11008), (5, 13824), (3, 22016), (33, 4096), (2, 2816)])
 def test_activate_quant(m, h):
     from atom_b200 import ops
@@ -158,8 +176,9 @@ def test_batch_decode(B, H, P, lens):
         o = ops.batch_decode_i4(T(q), kv, layer).cpu().numpy()
         ref = O.batch_decode_i4(q, data, param, indptr, indices, last, layer)
         # FP16 output of an FP32 softmax-attention with approximate-vs-exact transcendental differences:
-        # rtol/atol 1e-3 (the reference intends 5e-4 against an FP16 torch pipeline, test_batch_decode_int4.py:9-14)
-        assert np.allclose(o.astype(np.float32), ref.astype(np.float32), rtol=1e-3, atol=1e-3)
+        # rtol/atol 5e-4: the bound the reference's own test intends (test_batch_decode_int4.py:9-14), SURVEY.md 8(c) policy (4)
+        err = np.abs(o.astype(np.float32) - ref.astype(np.float32)) - 5e-4 * np.abs(ref.astype(np.float32))
+        assert err.max() <= 5e-4, f"layer {layer}: worst excess over rtol*|ref| = {err.max():.2e} (atol 5e-4)"
 
 
 def test_append_and_init_kv_bit_exact():

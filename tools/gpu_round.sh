@@ -30,5 +30,9 @@ for s in $STEPS; do case $s in
            timeout 300 python tools/gpu_check.py gtime 128 256 1024 4096 2>> $OUT/sk_gtime.err | tee $OUT/tall_gtime.jsonl
            : > $OUT/sk_trace.jsonl
            for cfg in "16 0" "16 1" "4096 0" "4096 256"; do timeout 120 python tools/gpu_check.py trace $cfg 2>&1 | tail -1 | tee -a $OUT/sk_trace.jsonl | cut -c1-2500; done ;;
+  dec)     echo "== decode attention: parity at 5e-4, timing, ncu capture"
+           timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py -m gpu -q --timeout=300 -p no:cacheprovider -k "decode or rmsnorm" > $OUT/pytest_dec.txt 2>&1; echo "rc=$?"; tail -15 $OUT/pytest_dec.txt
+           timeout 300 python tools/layer_bench.py 2>&1 | tail -1 | tee $OUT/layer_7b.json
+           timeout 300 ncu --set full --clock-control none --import-source on -k regex:batch_decode -s 2 -c 1 -f -o $OUT/prof_decode python tools/layer_bench.py --copies 1 > /dev/null 2>&1; ls -la $OUT/prof_decode.ncu-rep ;;
   *) echo "unknown step $s" ;;
 esac; done
