@@ -22,6 +22,8 @@ _SIGNATURES = {
     "atom_activate_fp16_i4": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "atom_gemm_i4_o16": (_I, [_P] * 9 + [_I64, _I64, _I64, _U32, _P]),
     "atom_gemm_i4_o4": (_I, [_P] * 10 + [_I64, _I64, _I64, _U32, _P]),
+    "atom_gemm_i4_qkv": (_I, [_P] * 13 + [_I64, _I64, _I64, _U32, _P]),
+    "atom_gemm_i4_gateup_act": (_I, [_P] * 12 + [_I64, _I64, _I64, _U32, _P]),
     "atom_gemm_set_trace": (_I, [_P]),
     "atom_set_pdl": (_I, [_I]),
     "atom_batch_decode_i4": (_I, [_P] * 7 + [_I] * 5 + [_P]),

@@ -249,7 +249,7 @@ bool gemm_pdl_enabled() {
 }
 
 template <int BN, int kSplit, int kEpi>
-int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
+int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream, int64_t out_channels = -1) {
   using C = atom::SkinnyCfg<BN, kSplit, kEpi>;
   auto kern = atom::gemm_i4_skinny_kernel<BN, kSplit, kEpi>;
   int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (skinny)", true);
@@ -259,7 +259,8 @@ int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream
   if ((rc = make_map(&tp4, op.b, kp, op.N, kp, 64, C::BM, 2))) return rc;
   if ((rc = make_map(&tp8, op.bk, 128, op.N, 128, 128, C::BM, 1))) return rc;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)((op.N + C::BM - 1) / C::BM), (unsigned)((op.M + BN - 1) / BN), kSplit);
+  const int64_t chan = out_channels > 0 ? out_channels : op.N;       // (gate/up: op.N = 2 I weight rows, I output channel tiles)
+  cfg.gridDim = dim3((unsigned)((chan + C::BM - 1) / C::BM), (unsigned)((op.M + BN - 1) / BN), kSplit);
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
@@ -393,7 +394,7 @@ int gemm_common(const void* a, const void* b, const void* a_scale, const void* b
   args.a_keeper_scale = (const __half*)a_keeper_scale; args.b_keeper_scale = (const __half*)b_keeper_scale;
   args.d = o4 ? nullptr : (__half*)d; args.d4 = o4 ? (uint8_t*)d : nullptr; args.d_scale = (__half2*)d_scale;
   args.M = (int)M; args.N = (int)N; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M); args.trace = g_trace;
-  args.a4 = (const uint8_t*)a; args.a8 = (const int8_t*)a_keeper;
+  args.a4 = (const uint8_t*)a; args.a8 = (const int8_t*)a_keeper; args.ldb_scale = (int)N;
   return o4 ? gemm_dispatch<true>(op, args, flags, (cudaStream_t)stream) : gemm_dispatch<false>(op, args, flags, (cudaStream_t)stream);
 }
 
@@ -471,6 +472,72 @@ int atom_gemm_i4_o16(const void* a, const void* b, const void* a_scale, const vo
                      int64_t N, int64_t K, uint32_t flags, void* stream) {
   return gemm_common(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, d, nullptr, M, N, K,
                      flags, stream, false);
+}
+
+int atom_gemm_i4_qkv(const void* a, const void* b_qkv, const void* a_scale, const void* b_scale_qkv, const void* a_keeper,
+                     const void* b_keeper_qkv, const void* a_keeper_scale, const void* b_keeper_scale_qkv, void* q, void* k,
+                     void* k_scale, void* v, void* v_scale, int64_t M, int64_t H, int64_t K, uint32_t flags, void* stream) {
+  (void)flags;
+  ATOM_REQUIRE(a && b_qkv && a_scale && b_scale_qkv && a_keeper && b_keeper_qkv && a_keeper_scale && b_keeper_scale_qkv && q && k &&
+               k_scale && v && v_scale, "gemm_i4_qkv: null pointer argument");
+  ATOM_REQUIRE(M > 0 && H > 0 && H % 128 == 0, "gemm_i4_qkv: M=%lld must be positive, H=%lld a positive multiple of 128", (long long)M, (long long)H);
+  ATOM_REQUIRE(K >= 256 && K % 128 == 0, "gemm_i4_qkv: K=%lld must be a multiple of 128 and >= 256", (long long)K);
+  ATOM_REQUIRE(aligned16(a) && aligned16(b_qkv) && aligned16(a_keeper) && aligned16(b_keeper_qkv) && aligned16(q) && aligned16(b_scale_qkv) &&
+               aligned16(b_keeper_scale_qkv), "gemm_i4_qkv: operand pointers must be 16-byte aligned");
+  ATOM_REQUIRE(M < (1ll << 31) && 3 * H < (1ll << 31) && K < (1ll << 24), "gemm_i4_qkv: dimension too large");
+  const int64_t N = 3 * H, kp = (K - 128) / 2;
+  atom::GemmArgs args{};
+  args.a_scale = (const __half*)a_scale; args.a_keeper_scale = (const __half*)a_keeper_scale;
+  args.M = (int)M; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M); args.trace = g_trace;
+  args.a4 = (const uint8_t*)a; args.a8 = (const int8_t*)a_keeper; args.ldb_scale = (int)N;
+  if (M <= 64) {
+    // one launch: 3H/128 channel tiles, the tile index selects the epilogue (q: FP16, k / v: asymmetric INT4 per head)
+    GemmOperands op{a, b_qkv, a_keeper, b_keeper_qkv, M, N, K};
+    args.b_scale = (const __half*)b_scale_qkv; args.b_keeper_scale = (const __half*)b_keeper_scale_qkv;
+    args.N = (int)N; args.seg_tiles = (int)(H / 128);
+    args.d = (__half*)q; args.d4 = (uint8_t*)k; args.d_scale = (__half2*)k_scale; args.d4_v = (uint8_t*)v; args.d_scale_v = (__half2*)v_scale;
+    if (M <= 16) return launch_skinny<16, 1, atom::EPI_QKV>(op, args, (cudaStream_t)stream);
+    if (M <= 32) return launch_skinny<32, 1, atom::EPI_QKV>(op, args, (cudaStream_t)stream);
+    return launch_skinny<64, 1, atom::EPI_QKV>(op, args, (cudaStream_t)stream);
+  }
+  // prefill sizes: three launches of the tall kernel on the row slices of the fused matrices
+  for (int seg = 0; seg < 3; ++seg) {
+    GemmOperands op{a, (const uint8_t*)b_qkv + (size_t)seg * H * kp, a_keeper, (const int8_t*)b_keeper_qkv + (size_t)seg * H * 128, M, H, K};
+    atom::GemmArgs sa = args;
+    sa.b_scale = (const __half*)b_scale_qkv + (size_t)seg * H; sa.b_keeper_scale = (const __half*)b_keeper_scale_qkv + (size_t)seg * H;
+    sa.N = (int)H;
+    int rc;
+    if (seg == 0) { sa.d = (__half*)q; rc = launch_tall<false>(op, sa, (cudaStream_t)stream); }
+    else { sa.d4 = (uint8_t*)(seg == 1 ? k : v); sa.d_scale = (__half2*)(seg == 1 ? k_scale : v_scale); rc = launch_tall<true>(op, sa, (cudaStream_t)stream); }
+    if (rc) return rc;
+  }
+  return ATOM_OK;
+}
+
+int atom_gemm_i4_gateup_act(const void* a, const void* b_gu, const void* a_scale, const void* b_scale_gu, const void* a_keeper,
+                            const void* b_keeper_gu, const void* a_keeper_scale, const void* b_keeper_scale_gu, void* o_outliers,
+                            void* o_norms, void* outlier_scales, void* norm_scales, int64_t M, int64_t I, int64_t K, uint32_t flags,
+                            void* stream) {
+  (void)flags;
+  ATOM_REQUIRE(a && b_gu && a_scale && b_scale_gu && a_keeper && b_keeper_gu && a_keeper_scale && b_keeper_scale_gu && o_outliers &&
+               o_norms && outlier_scales && norm_scales, "gemm_i4_gateup_act: null pointer argument");
+  ATOM_REQUIRE(M > 0 && I >= 256 && I % 128 == 0, "gemm_i4_gateup_act: M=%lld must be positive, I=%lld a multiple of 128 >= 256", (long long)M, (long long)I);
+  ATOM_REQUIRE(K >= 256 && K % 128 == 0, "gemm_i4_gateup_act: K=%lld must be a multiple of 128 and >= 256", (long long)K);
+  ATOM_REQUIRE(aligned16(a) && aligned16(b_gu) && aligned16(a_keeper) && aligned16(b_keeper_gu) && aligned16(b_scale_gu) &&
+               aligned16(b_keeper_scale_gu), "gemm_i4_gateup_act: operand pointers must be 16-byte aligned");
+  ATOM_REQUIRE(2 * I < (1ll << 31) && K < (1ll << 24), "gemm_i4_gateup_act: dimension too large");
+  if (M > 64) return fail(ATOM_E_UNSUPPORTED, "gemm_i4_gateup_act: fused epilogue exists for decode batches (M <= 64) only; "
+                                              "run the two projections and activate_fp16_i4 for M=%lld", (long long)M);
+  GemmOperands op{a, b_gu, a_keeper, b_keeper_gu, M, 2 * I, K};
+  atom::GemmArgs args{};
+  args.a_scale = (const __half*)a_scale; args.a_keeper_scale = (const __half*)a_keeper_scale;
+  args.b_scale = (const __half*)b_scale_gu; args.b_keeper_scale = (const __half*)b_keeper_scale_gu;
+  args.M = (int)M; args.N = (int)(2 * I); args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M); args.trace = g_trace;
+  args.a4 = (const uint8_t*)a; args.a8 = (const int8_t*)a_keeper; args.ldb_scale = (int)(2 * I); args.gu_rows = (int)I;
+  args.q8_out = (int8_t*)o_outliers; args.q4_out = (uint8_t*)o_norms; args.q8_scale = (__half*)outlier_scales; args.q4_scale = (__half*)norm_scales;
+  if (M <= 16) return launch_skinny<16, 2, atom::EPI_GATEUP>(op, args, (cudaStream_t)stream, I);
+  if (M <= 32) return launch_skinny<32, 2, atom::EPI_GATEUP>(op, args, (cudaStream_t)stream, I);
+  return launch_skinny<64, 2, atom::EPI_GATEUP>(op, args, (cudaStream_t)stream, I);
 }
 
 int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,

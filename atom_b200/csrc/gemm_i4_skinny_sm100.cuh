@@ -32,7 +32,12 @@
 
 namespace atom {
 
-enum { EPI_O16 = 0, EPI_O4 = 1 };
+// EPI_QKV: fused q/k/v projection (o16 for the q tiles, o4 for the k and v tiles).
+// EPI_GATEUP: fused gate/up projection: a cluster of two CTAs (rank 0 = the gate tile, rank 1 = the up tile of the same 128
+// channels, each streaming the whole K range); rank 1 hands its FP32 sums to rank 0 through DSMEM, rank 0 applies
+// SiLU(gate) * up and the dynamic per-(token, 128-channel group) quantisation of activate_fp16_i4 and writes the INT4 / INT8
+// operands of the down projection directly: no FP16 round trip through HBM, no activation kernel.
+enum { EPI_O16 = 0, EPI_O4 = 1, EPI_QKV = 2, EPI_GATEUP = 3 };
 
 template <int BN, int kSplit, int kEpi>
 struct SkinnyCfg {
@@ -46,13 +51,13 @@ struct SkinnyCfg {
   static constexpr int A_PAIRS = ONE_PER_SM ? 4 : (BN == 16 ? 3 : 2);   // tensor-memory operand slots (2 groups = 64 columns each)
   static constexpr int ACC_PAIRS = 2;                  // accumulator slots (2 groups = 2 * BN columns each)
   static constexpr int A_COL0 = 0, ACC_COL0 = A_PAIRS * 64;
-  static constexpr int PACK = ONE_PER_SM ? 8 : (BN == 16 ? 6 : 5);   // packed weight ring depth (groups)
+  static constexpr int PACK = ONE_PER_SM ? 8 : (BN == 16 ? 6 : (kEpi == EPI_GATEUP ? 4 : 5));   // packed weight ring depth (groups)
   static constexpr int QB = 4, QS = 2 * QB;            // token tiles: groups per hand-off, expanded slots
   static constexpr int SC = BN == 16 ? 32 : 16;        // groups per staged scale chunk
   static constexpr int THREADS = 384;                  // 4 service warps, 4 converter warps, 4 epilogue warps
   static constexpr int PACK_P = BM * 64;
   static constexpr int EXP_Q = (BN * 128 + 1023) / 1024 * 1024;
-  static constexpr int CPR = BN / kSplit;              // token columns reduced + stored by one split-K rank
+  static constexpr int CPR = kEpi == EPI_GATEUP ? BN : BN / kSplit;   // token columns reduced + stored by one split-K rank (gate/up: all of them go to rank 0)
   static constexpr int OFF_PACK_P = 0;
   static constexpr int OFF_EXP_Q = OFF_PACK_P + PACK * PACK_P;
   static constexpr int OFF_KEEP_P = OFF_EXP_Q + QS * EXP_Q;
@@ -62,14 +67,14 @@ struct SkinnyCfg {
   static constexpr int RED_BYTES = BM * CPR * 4;                       // one source rank's partial for this rank's columns
   static constexpr int OFF_RED = OFF_SA + SC * BN * 2;
   static constexpr int OFF_XCH = OFF_RED + (kSplit > 1 ? (kSplit - 1) * RED_BYTES : 0);   // o4: per-warp |v| min/max
-  static constexpr int OFF_BAR = OFF_XCH + (kEpi == EPI_O4 ? 8 * BN * 4 : 0);
+  static constexpr int OFF_BAR = OFF_XCH + (kEpi != EPI_O16 ? 8 * BN * 4 : 0);     // gate/up uses the first 4 * BN floats
   static constexpr int NUM_BARS = 2 * PACK + 2 * A_PAIRS + 4 + ACC_PAIRS + 3;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
   static constexpr int CTAS_PER_SM = ONE_PER_SM ? 1 : 2;
   static_assert(BN == 16 || BN == 32 || BN == 64, "token tile");
   static_assert(BN % kSplit == 0 && CPR >= 4, "every split-K rank owns at least 4 token columns");
-  static_assert(kEpi == EPI_O16 || kSplit == 1, "the INT4-output epilogue quantises un-split FP32 sums");
+  static_assert(kEpi == EPI_O16 || (kEpi == EPI_GATEUP && kSplit == 2) || kSplit == 1, "the quantising epilogues work on un-split FP32 sums");
   static_assert(A_PAIRS * 64 + ACC_PAIRS * 2 * BN <= TMEM_COLS, "tensor memory budget");
   static_assert(A_PAIRS >= ACC_PAIRS, "mma_done is indexed by operand slot");
   static_assert(ONE_PER_SM ? SMEM_BYTES <= 227 * 1024 : SMEM_BYTES <= 113 * 1024, "shared memory budget (two CTAs per SM)");
@@ -146,10 +151,14 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   uint32_t krank = 0;
   if constexpr (kSplit > 1) {
     krank = cluster_ctarank();
-    const int per = (total_groups + kSplit - 1) / kSplit;
-    g_begin = min((int)krank * per, total_groups);
-    g_end = min(g_begin + per, total_groups);
+    if constexpr (kEpi != EPI_GATEUP) {
+      const int per = (total_groups + kSplit - 1) / kSplit;
+      g_begin = min((int)krank * per, total_groups);
+      g_end = min(g_begin + per, total_groups);
+    }
   }
+  // gate/up: the two ranks are not K slices but the gate (rank 0) and up (rank 1) rows of the same channel tile
+  const int wrow0 = n0 + (kEpi == EPI_GATEUP ? (int)krank * args.gu_rows : 0);    // first row of this CTA's weight tile
   const int iters = g_end - g_begin;                                  // groups of this CTA, the keeper (if any) last
   const int n4 = max(0, min(g_end, args.G) - g_begin);                // ... of which INT4
   const bool has_keeper = n4 < iters;
@@ -169,13 +178,13 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       fence_barrier_init();
       for (int i = 0; i < first; ++i) {
         mbar_arrive_expect_tx(&pack_full[i], C::PACK_P);
-        tma_load_2d(smem + C::OFF_PACK_P + i * C::PACK_P, &tm_p4, &pack_full[i], (g_begin + i) * 64, n0);
+        tma_load_2d(smem + C::OFF_PACK_P + i * C::PACK_P, &tm_p4, &pack_full[i], (g_begin + i) * 64, wrow0);
         if (i < 8) trace_stamp(args, 8 + i);
       }
       if (has_keeper) {
         tma_prefetch_desc(&tm_p8);
         mbar_arrive_expect_tx(keep_full, C::BM * 128);
-        tma_load_2d(smem + C::OFF_KEEP_P, &tm_p8, keep_full, 0, n0);
+        tma_load_2d(smem + C::OFF_KEEP_P, &tm_p8, keep_full, 0, wrow0);
       }
     }
     __syncwarp();
@@ -187,7 +196,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     mbar_init(kq_full, 2);
     mbar_init(red_full, 1);
     fence_barrier_init();
-    if constexpr (kSplit > 1) mbar_arrive_expect_tx(red_full, (kSplit - 1) * C::RED_BYTES);
+    if constexpr (kSplit > 1) mbar_arrive_expect_tx(red_full, (kSplit - 1) * C::RED_BYTES);   // (gate/up: only rank 0 ever waits on it)
   } else if (warp == 2) {
     tmem_alloc<C::TMEM_COLS>(tmem_ptr);
   }
@@ -205,7 +214,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       mbar_wait(&pack_empty[ps], ((i / C::PACK) & 1) ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&pack_full[ps], C::PACK_P);
-        tma_load_2d(smem + C::OFF_PACK_P + ps * C::PACK_P, &tm_p4, &pack_full[ps], (g_begin + i) * 64, n0);
+        tma_load_2d(smem + C::OFF_PACK_P + ps * C::PACK_P, &tm_p4, &pack_full[ps], (g_begin + i) * 64, wrow0);
         if (i < 8) trace_stamp(args, 8 + i);
       }
       __syncwarp();
@@ -360,9 +369,9 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
         if (u > 0) asm volatile("bar.sync 2, 128;" ::: "memory");        // everyone is done with the previous chunk
         for (int c = te; c < cnt * 16; c += 128) {
           const int gi = c >> 4, part = c & 15, g = g_begin + i0 + gi;
-          const __half* bs_row = (g == args.G) ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
+          const __half* bs_row = (g == args.G) ? args.b_keeper_scale : args.b_scale + (size_t)g * args.ldb_scale;
           uint4 v = make_uint4(0, 0, 0, 0);
-          if (n0 + 8 * part < args.N) v = ld_nc_v4(bs_row + n0 + 8 * part);
+          if (n0 + 8 * part < (kEpi == EPI_GATEUP ? args.gu_rows : args.N)) v = ld_nc_v4(bs_row + wrow0 + 8 * part);
           reinterpret_cast<uint4*>(sb_s)[c] = v;
         }
         if (u == 0) griddep_wait();
@@ -428,7 +437,63 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     if (warp == 8 && lane == 0) trace_stamp(args, 2);
     constexpr float kInv = 1.0f / 256.0f;   // exact: removes the 16 * 16 operand factor
 
-    if constexpr (kEpi == EPI_O16) {
+    if constexpr (kEpi == EPI_GATEUP) {
+      cluster_wait();                        // pairs with the setup arrive: both CTAs of the pair are running
+      if (krank == 1) {
+        // ---------------------------------------------------------- up tile: hand the FP32 sums to the gate CTA
+        const uint32_t remote = mapa_shared(smem_u32(smem + C::OFF_RED), 0) + row * (BN * 4);
+        const uint32_t rbar = mapa_shared(smem_u32(red_full), 0);
+#pragma unroll
+        for (int c = 0; c < BN; c += 4) st_async_v4(remote + c * 4, acc[c], acc[c + 1], acc[c + 2], acc[c + 3], rbar);
+      } else {
+        // ---------------------------------------------------------- gate tile: SiLU(gate) * up, then the dynamic
+        // quantisation of activate_fp16_i4 (Activate.cuh:102-166) for this 128-channel group of every token.  Both
+        // projections are rounded to FP16 first, as they are when the reference stores them between the kernels.
+        mbar_wait(red_full, 0);
+        const float* red = reinterpret_cast<const float*>(smem + C::OFF_RED);
+        float* xmx = reinterpret_cast<float*>(smem + C::OFF_XCH);   // [4 warps][BN]
+        const bool last = ((int)blockIdx.x == args.gu_rows / 128 - 1);          // the INT8 keeper group of the down projection
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          const float g = __half2float(__float2half_rn(acc[c] * kInv));
+          const float up = __half2float(__float2half_rn(red[row * BN + c] * kInv));
+          const float t = silu_ref(g) * up;
+          acc[c] = t;
+          uint32_t ua = __float_as_uint(fabsf(t));
+          if (n0 + row >= args.gu_rows) ua = 0u;
+          ua = __reduce_max_sync(0xffffffffu, ua);        // |t| >= 0: IEEE bit patterns order like unsigned integers
+          if (lane == 0) xmx[wq * BN + c] = __uint_as_float(ua);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const size_t q4_pitch = (size_t)(args.gu_rows - 128) / 2;
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          const int m = m0 + c;
+          float maxv = fmaxf(fmaxf(xmx[c], xmx[BN + c]), fmaxf(xmx[2 * BN + c], xmx[3 * BN + c]));
+          maxv = maxv / (last ? 127.f : 7.f);                      // IEEE division, as `maxv /= 7`
+          const float r_scale = 1.f / maxv;
+          const int tq = (int)roundf(acc[c] * r_scale);            // round half away from zero (CUDA round())
+          const int q = last ? max(-128, min(127, tq)) : max(-8, min(7, tq));
+          const int qn = __shfl_down_sync(0xffffffffu, q, 1);      // channel n+1 lives in the next lane
+          if (m < args.M && n0 + row < args.gu_rows) {
+            if (last) args.q8_out[(size_t)m * 128 + row] = (int8_t)q;
+            else if ((lane & 1) == 0) args.q4_out[(size_t)m * q4_pitch + (size_t)blockIdx.x * 64 + (row >> 1)] = (uint8_t)((q & 0xF) | ((qn & 0xF) << 4));
+            if (row == 0) {
+              const __half hs = __float2half_rn(maxv);
+              __half* dst = last ? args.q8_scale : args.q4_scale + (size_t)blockIdx.x * args.lda_scale;
+              const int si = scale_index(m);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[si + 2 * j] = hs;     // replicated x4 (ldmatrix layout of the reference GEMM)
+            }
+          }
+        }
+      }
+    } else {
+    // fused q/k/v: the channel tile decides the epilogue (uniform per CTA)
+    const int seg = kEpi == EPI_QKV ? (int)blockIdx.x / args.seg_tiles : 0;
+    const int tile = kEpi == EPI_QKV ? (int)blockIdx.x % args.seg_tiles : (int)blockIdx.x;
+    const int n_out_dim = kEpi == EPI_QKV ? args.seg_tiles * 128 : args.N;       // row length of the output this tile writes
+    if (kEpi == EPI_O16 || (kEpi == EPI_QKV && seg == 0)) {
       // ---------------------------------------------------------- split-K: rank d reduces + stores token columns
       // [d * CPR, (d + 1) * CPR).  Partials travel as st.async messages that also complete transaction bytes on the
       // owner's mbarrier: no cluster barrier, and the owner sums in rank order 0..kSplit-1 (deterministic).
@@ -466,18 +531,20 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
         }
       }
       if (warp == 8 && lane == 0) trace_stamp(args, 3);
-      const int n = n0 + row;
-      if (n < args.N) {
+      const int n = tile * C::BM + row;
+      if (n < n_out_dim && n0 + row < args.N) {
 #pragma unroll
         for (int c = 0; c < BN; ++c) {
           const int m = m0 + c;
           if ((kSplit == 1 || c / C::CPR == (int)krank) && m < args.M)
-            args.d[(size_t)m * args.N + n] = __float2half_rn(acc[c] * kInv);      // a warp writes 64-B runs
+            args.d[(size_t)m * n_out_dim + n] = __float2half_rn(acc[c] * kInv);      // a warp writes 64-B runs
         }
       }
     } else {
       // ---------------------------------------------------------- o4 (DenseLayerGEMM_i4_o4.cu:705-787): per (token,
       // 128-channel head) asymmetric INT4 with the reference's |v| min/max; thread = channel, reduce over the 128 rows
+      uint8_t* d4 = (kEpi == EPI_QKV && seg == 2) ? args.d4_v : args.d4;
+      __half2* d_scale = (kEpi == EPI_QKV && seg == 2) ? args.d_scale_v : args.d_scale;
       float* xmx = reinterpret_cast<float*>(smem + C::OFF_XCH);   // [4 warps][BN]
       float* xmn = xmx + 4 * BN;
 #pragma unroll
@@ -491,7 +558,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
         if (lane == 0) { xmx[wq * BN + c] = __uint_as_float(umx); xmn[wq * BN + c] = __uint_as_float(umn); }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int n = n0 + row;
+      const int n = tile * C::BM + row;
 #pragma unroll
       for (int c = 0; c < BN; ++c) {
         const int m = m0 + c;
@@ -500,12 +567,13 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
         const float scale = (mx - mn) / 15.f, zero = -mn, r_scale = 1.f / scale;
         const int q = (int)roundf((acc[c] + zero) * r_scale) & 0xF;
         const int qn = __shfl_down_sync(0xffffffffu, q, 1);     // channel n+1 lives in the next lane
-        if (m < args.M && n < args.N) {
-          if ((lane & 1) == 0) args.d4[(size_t)m * (args.N / 2) + n / 2] = (uint8_t)(q | (qn << 4));
-          if (row == 0) args.d_scale[(size_t)m * (args.N / 128) + blockIdx.x] = __floats2half2_rn(scale, zero);
+        if (m < args.M && n < n_out_dim && n0 + row < args.N) {
+          if ((lane & 1) == 0) d4[(size_t)m * (n_out_dim / 2) + n / 2] = (uint8_t)(q | (qn << 4));
+          if (row == 0) d_scale[(size_t)m * (n_out_dim / 128) + tile] = __floats2half2_rn(scale, zero);
         }
       }
     }
+    }   // !EPI_GATEUP
   }
 
   // ---------------------------------------------------------------- teardown

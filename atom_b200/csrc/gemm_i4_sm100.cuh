@@ -36,6 +36,13 @@ struct GemmArgs {
   __half* d;                     // o16: [M][N]
   uint8_t* d4;                   // o4 : [M][N/2]
   __half2* d_scale;              // o4 : [M][N/128] (scale, zero)
+  uint8_t* d4_v;                 // fused q/k/v projection (decode kernel, EPI_QKV): channel tiles [0, seg_tiles) are q -> d (o16),
+  __half2* d_scale_v;            //   [seg_tiles, 2 seg_tiles) are k -> d4 / d_scale (o4), the rest v -> d4_v / d_scale_v (o4)
+  int seg_tiles;
+  // fused gate/up projection + SiLU(gate)*up + dynamic quantisation (decode kernel, EPI_GATEUP): the activation 4-tuple
+  // that activate_fp16_i4 would have produced (Activate.cuh:67-180); gu_rows = intermediate size I (up rows start at I)
+  int8_t* q8_out; uint8_t* q4_out; __half* q8_scale; __half* q4_scale; int gu_rows;
+  int ldb_scale;                 // pitch (halves) of the b_scale rows; N unless the weights are a slice of a fused matrix
   int M, N, G;                   // G = number of INT4 groups = K/128 - 1
   int lda_scale;                 // S(M)
   unsigned long long* trace;     // optional device buffer [ctas][128] of clock64 stamps (atom_gemm_set_trace), else null
@@ -57,6 +64,7 @@ __device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
   }
 }
 
+__device__ __forceinline__ float silu_ref(float x) { return x / (1.0f + expf(-x)); }   // Activate.cuh:28
 __host__ __device__ __forceinline__ int scale_index(int row) { return (row / 16) * 64 + (row % 8) * 8 + ((row / 8) % 2); }
 __host__ __device__ __forceinline__ int scale_size(int m) { return m / 16 * 64 + 64 - (1 - (m % 16) / 8) * (8 - (m % 8)) * 8; }
 

@@ -199,7 +199,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
             const int g = s * GS + j;
             const bool keeper = (g == args.G);
             const __half* as_row = keeper ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
-            const __half* bs_row = keeper ? args.b_keeper_scale : args.b_scale + (size_t)g * args.N;
+            const __half* bs_row = keeper ? args.b_keeper_scale : args.b_scale + (size_t)g * args.ldb_scale;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int w = lane + 32 * h, blk = w >> 3, i = w & 7;

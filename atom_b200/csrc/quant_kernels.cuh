@@ -161,7 +161,6 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ re
 
 // ---------------------------------------------------------------- K5: SiLU(a) * b + quantise (no reorder)
 // one warp per (row, group); 8 warps per block, flattened over rows x groups.
-__device__ __forceinline__ float silu_ref(float x) { return x / (1.0f + expf(-x)); }   // Activate.cuh:28
 
 __global__ void __launch_bounds__(256)
 activate_quant_kernel(const __half* __restrict__ a, const __half* __restrict__ b, int seq_len, int hidden,

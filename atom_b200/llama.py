@@ -83,6 +83,31 @@ class LinearInt4(nn.Module):
                  flags=flags)
 
 
+@torch.no_grad()
+def fuse_linear_rows(layers):
+    """Row-concatenate LinearInt4 layers that share their input (q/k/v or gate/up) for the fused decode launches
+    (ops.dense_layer_gemm_i4_qkv / _gateup_act).  The big tensors are shared, not duplicated: every layer's weight_int4 /
+    weight_int8 becomes a row-slice VIEW of the fused tensor; only the (small) scales exist twice, because a slice of the
+    fused [G, sum N] scale matrix has the wrong pitch for the single-projection kernels."""
+    k = layers[0].in_features
+    g = k // 128 - 1
+    assert all(l.in_features == k for l in layers)
+    w4 = torch.cat([l.weight_int4.data for l in layers], 0).contiguous()
+    w8 = torch.cat([l.weight_int8.data for l in layers], 0).contiguous()
+    s4 = torch.cat([l.scale_int4.data.reshape(-1)[: g * l.out_features].view(g, l.out_features) for l in layers], 1).contiguous()
+    s8 = torch.cat([l.scale_int8.data[: l.out_features] for l in layers], 0).contiguous()
+    r = 0
+    for l in layers:
+        l.weight_int4 = nn.Parameter(w4[r:r + l.out_features], requires_grad=False)
+        l.weight_int8 = nn.Parameter(w8[r:r + l.out_features], requires_grad=False)
+        r += l.out_features
+    return w4, s4, w8, s8
+
+
+def _capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def run_concurrently(layers, x):
     """Decode-sized batches: the GEMMs that share one input (q/k/v, gate/up) are independent and each too small to fill
     the GPU, so they run side by side on forked streams, un-split along K (a 4096-channel projection is then 32 CTAs);
@@ -117,8 +142,20 @@ class LlamaMLP(nn.Module):
         self.gate_proj = LinearInt4(self.hidden_size, self.intermediate_size, out_dtype="fp16")
         self.up_proj = LinearInt4(self.hidden_size, self.intermediate_size, out_dtype="fp16")
         self.down_proj = LinearInt4(self.intermediate_size, self.hidden_size, out_dtype="fp16")
+        self._gu = None        # fused [gate; up] operands, built by fuse()
+
+    def fuse(self):
+        """One launch for gate_proj + up_proj + SiLU*mul + quantise on decode batches (call after the weights are loaded)."""
+        self._gu = fuse_linear_rows([self.gate_proj, self.up_proj])
+        return self
 
     def forward(self, x):
+        if x[1].shape[0] <= 64 and self._gu is None and not _capturing():
+            self.fuse()
+        if x[1].shape[0] <= 64 and self._gu is not None:
+            outlier, norms, outlier_scales, norm_scales = x
+            w4, s4, w8, s8 = self._gu
+            return self.down_proj(ops.dense_layer_gemm_i4_gateup_act(norms, w4, norm_scales, s4, outlier, w8, outlier_scales, s8))
         gate, up = run_concurrently([self.gate_proj, self.up_proj], x)
         return self.down_proj(ops.activate_fp16_i4(gate, up))
 
@@ -152,11 +189,24 @@ class LlamaAttention(nn.Module):
         self.v_proj = LinearInt4(self.hidden_size, h, out_dtype="int4")
         self.o_proj = LinearInt4(h, self.hidden_size, out_dtype="fp16")
         self.reorder_index = nn.Parameter(torch.randperm(self.hidden_size, dtype=torch.int16), requires_grad=False)
+        self._qkv = None       # fused [q; k; v] operands, built by fuse()
+
+    def fuse(self):
+        """One launch for the q, k and v projections (call after the weights are loaded)."""
+        self._qkv = fuse_linear_rows([self.q_proj, self.k_proj, self.v_proj])
+        return self
 
     def forward(self, hidden_states, blen: BatchLenInfo, prefill_kv, decode_kv) -> torch.Tensor:
         nvtx = torch.cuda.nvtx
         nvtx.range_push("qkv_proj")
-        q_proj, k_proj, v_proj = run_concurrently([self.q_proj, self.k_proj, self.v_proj], hidden_states)
+        if self._qkv is None and not _capturing():
+            self.fuse()
+        if self._qkv is not None:
+            outlier, norms, outlier_scales, norm_scales = hidden_states
+            w4, s4, w8, s8 = self._qkv
+            q_proj, k_proj, v_proj = ops.dense_layer_gemm_i4_qkv(norms, w4, norm_scales, s4, outlier, w8, outlier_scales, s8)
+        else:
+            q_proj, k_proj, v_proj = run_concurrently([self.q_proj, self.k_proj, self.v_proj], hidden_states)
         nvtx.range_pop()
         stack = []
         nh, hd = self.num_heads, self.head_dim
@@ -212,6 +262,10 @@ class LlamaRMSNormInt4(nn.Module):
     def forward(self, hidden_states):
         return ops.rmsnorm_fp16_i4(hidden_states, self.weight, self.reorder_index, self.variance_epsilon)
 
+    def forward_add(self, hidden_states, residual):
+        """(residual + hidden_states, norm+quantise of that sum) in one launch."""
+        return ops.add_rmsnorm_fp16_i4(hidden_states, residual, self.weight, self.reorder_index, self.variance_epsilon)
+
 
 class LlamaDecoderLayer(nn.Module):
     """llama.py:248-292"""
@@ -227,17 +281,31 @@ class LlamaDecoderLayer(nn.Module):
     def init_random(self, seed=0):
         for i, m in enumerate(mod for mod in self.modules() if isinstance(mod, LinearInt4)):
             m.init_random(seed * 16 + i)
+        if self.self_attn.q_proj.weight_int4.is_cuda:
+            self.fuse()
+        return self
+
+    def fuse(self):
+        """Build the fused q/k/v and gate/up operands (weights already on the GPU)."""
+        self.self_attn.fuse()
+        self.mlp.fuse()
         return self
 
     def forward(self, hidden_states, blen: BatchLenInfo, prefill_kv, decode_kv) -> torch.Tensor:
-        residual = hidden_states
-        hidden_states = self.input_layernorm(hidden_states)
-        hidden_states = self.self_attn(hidden_states, blen, prefill_kv, decode_kv)
-        hidden_states = residual + hidden_states
-        residual = hidden_states
-        hidden_states = self.post_attention_layernorm(hidden_states)
-        hidden_states = self.mlp(hidden_states)
-        return residual + hidden_states
+        hidden_states, delta = self.forward_residual(hidden_states, None, blen, prefill_kv, decode_kv)
+        return hidden_states + delta
+
+    def forward_residual(self, residual, delta, blen: BatchLenInfo, prefill_kv, decode_kv):
+        """The layer on a (residual, delta) pair whose sum is the hidden state: every `residual + x` of the reference's layer
+        (llama.py:266-292) is folded into the RMSNorm+quantise launch that follows it (ops.add_rmsnorm_fp16_i4), including
+        the one that closes the PREVIOUS layer.  Returns the pair for the next layer; LlamaModel adds the last one."""
+        if delta is None:
+            x = self.input_layernorm(residual)
+        else:
+            residual, x = self.input_layernorm.forward_add(delta, residual)
+        attn = self.self_attn(x, blen, prefill_kv, decode_kv)
+        residual, x = self.post_attention_layernorm.forward_add(attn, residual)
+        return residual, self.mlp(x)
 
 
 class LlamaRMSNorm(nn.Module):
@@ -262,10 +330,10 @@ class LlamaModel(nn.Module):
         self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
     def forward(self, input_ids, blen, prefill_kv, decode_kv):
-        h = self.embed_tokens(input_ids)
+        h, delta = self.embed_tokens(input_ids), None
         for layer in self.layers:
-            h = layer(h, blen, prefill_kv, decode_kv)
-        return self.norm(h)
+            h, delta = layer.forward_residual(h, delta, blen, prefill_kv, decode_kv)
+        return self.norm(h + delta if delta is not None else h)
 
 
 class LlamaForCausalLM(nn.Module):

@@ -158,6 +158,50 @@ def dense_layer_gemm_i4_o4(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_
     return d, d_scale
 
 
+def dense_layer_gemm_i4_qkv(a, b_qkv, a_scale, b_scale_qkv, a_keeper, b_keeper_qkv, a_keeper_scale, b_keeper_scale_qkv, flags=GEMM_AUTO):
+    """EXTENSION: q (fp16), k and v (o4) projections of one input over row-concatenated weights [3H, ...] in one launch for
+    decode batches.  Returns (q, (k, k_scale), (v, v_scale)), bit-identical to the three separate operator calls."""
+    _req_width("dense_layer_gemm_i4_qkv", a_1=a, b_qkv_1=b_qkv, f16_a_scale_2=a_scale, f16_b_scale_qkv_2=b_scale_qkv, a_keeper_1=a_keeper,
+               b_keeper_qkv_1=b_keeper_qkv, f16_a_keeper_scale_2=a_keeper_scale, f16_b_keeper_scale_qkv_2=b_keeper_scale_qkv)
+    _req_cuda(a, b_qkv, a_scale, b_scale_qkv, a_keeper, b_keeper_qkv, a_keeper_scale, b_keeper_scale_qkv)
+    m, n3 = a.size(0), b_qkv.size(0)
+    k = a.size(1) * 2 + a_keeper.size(1)
+    if n3 % 384 != 0 or b_scale_qkv.numel() < (k // 128 - 1) * n3 or b_keeper_qkv.size(0) != n3:
+        raise RuntimeError("dense_layer_gemm_i4_qkv: weights must be the row concatenation [q; k; v] with H % 128 == 0")
+    h = n3 // 3
+    q = torch.empty((m, h), dtype=torch.float16, device=a.device)
+    kk = torch.empty((m, h // 2), dtype=torch.uint8, device=a.device)
+    vv = torch.empty((m, h // 2), dtype=torch.uint8, device=a.device)
+    ks = torch.empty((m, h // 128 * 2), dtype=torch.float16, device=a.device)
+    vs = torch.empty((m, h // 128 * 2), dtype=torch.float16, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().atom_gemm_i4_qkv(a.data_ptr(), b_qkv.data_ptr(), a_scale.data_ptr(), b_scale_qkv.data_ptr(),
+                                               a_keeper.data_ptr(), b_keeper_qkv.data_ptr(), a_keeper_scale.data_ptr(),
+                                               b_keeper_scale_qkv.data_ptr(), q.data_ptr(), kk.data_ptr(), ks.data_ptr(), vv.data_ptr(),
+                                               vs.data_ptr(), m, h, k, flags, _stream(a)), "dense_layer_gemm_i4_qkv")
+    return q, (kk, ks), (vv, vs)
+
+
+def dense_layer_gemm_i4_gateup_act(a, b_gu, a_scale, b_scale_gu, a_keeper, b_keeper_gu, a_keeper_scale, b_keeper_scale_gu, flags=GEMM_AUTO):
+    """EXTENSION: activate_fp16_i4(gate_proj(x), up_proj(x)) in one launch over row-concatenated weights [2I, ...] (decode
+    batches, M <= 64).  Returns the activation 4-tuple, bit-identical to the three separate operator calls."""
+    _req_width("dense_layer_gemm_i4_gateup_act", a_1=a, b_gu_1=b_gu, f16_a_scale_2=a_scale, f16_b_scale_gu_2=b_scale_gu, a_keeper_1=a_keeper,
+               b_keeper_gu_1=b_keeper_gu, f16_a_keeper_scale_2=a_keeper_scale, f16_b_keeper_scale_gu_2=b_keeper_scale_gu)
+    _req_cuda(a, b_gu, a_scale, b_scale_gu, a_keeper, b_keeper_gu, a_keeper_scale, b_keeper_scale_gu)
+    m, n2 = a.size(0), b_gu.size(0)
+    k = a.size(1) * 2 + a_keeper.size(1)
+    if n2 % 256 != 0 or b_keeper_gu.size(0) != n2:
+        raise RuntimeError("dense_layer_gemm_i4_gateup_act: weights must be the row concatenation [gate; up] with I % 128 == 0")
+    inter = n2 // 2
+    out = _quant_outputs(m, inter, a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().atom_gemm_i4_gateup_act(a.data_ptr(), b_gu.data_ptr(), a_scale.data_ptr(), b_scale_gu.data_ptr(),
+                                                      a_keeper.data_ptr(), b_keeper_gu.data_ptr(), a_keeper_scale.data_ptr(),
+                                                      b_keeper_scale_gu.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                                      out[3].data_ptr(), m, inter, k, flags, _stream(a)), "dense_layer_gemm_i4_gateup_act")
+    return out
+
+
 def _kv_dims(kv):
     # CHECK_DIM(6, kv_data) etc., punica_ops.cc:93-112
     if kv.data.dim() != 6 or kv.param.dim() != 6:

@@ -5,6 +5,13 @@ group 128, INT8 keeper 128, on synthetic random-quantised operands.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--m M]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
+Besides the headline line this also reports, in the same JSON object:
+  "sweep": the reference's nvbench axis (bench_dense_layer_gemm_i4_o16.cu:64-69) at M = 16 / 256 / 1024 / 4096, each against
+           min(HBM, tensor) roofline;
+  "tp":    BASELINE config #5 -- one decode step of a Llama-65B-shaped W4A4 decoder layer, tensor-parallel over the N
+           ranks of this run (N = 1: the whole layer on one GPU), one CUDA graph per step with the two all-reduces of the
+           layer INSIDE the timed region -> tokens/s at 80 layers (strong scaling: the work is fixed, N grows).
+
 One "step" = one pass of the hot path over one batch of synthetic input: `gemms_per_step` independent GEMM problems
 (distinct operand sets, together larger than the 126 MB L2, so every launch streams its weights from HBM), launched
 back to back from one CUDA graph.  `value` = whole-job TOP/s with operands resident in HBM (OP = 2*M*N*K, the
@@ -107,6 +114,128 @@ def ncu_traffic(m):
         return None
 
 
+def graph_time_us(fn, nsets, launches, reps, dev):
+    """Median device time per launch: `launches` calls of fn(i) captured in one CUDA graph, replayed `reps` times."""
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        for i in range(min(nsets, launches)):
+            fn(i)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for i in range(launches):
+                fn(i)
+        for _ in range(3):
+            g.replay()
+        st.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st); g.replay(); e1.record(st); e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / launches)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm_sweep(dev, peaks, ms=(16, 256, 1024, 4096), n=4096, k=4096):
+    """bench_gemm_i4_o16 axis: device time per GEMM (graph replay over operand sets larger than L2) and the roofline
+    fraction against min(HBM, tensor) with the measured denominators."""
+    from atom_b200 import ops, synth
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tc = 2.0 * peaks.get("bf16_tflops", 1590.0)
+    out = []
+    for m in ms:
+        one = synth.gemm_operands(m, n, k, dev, seed=99 + m)
+        per_set = sum(t.numel() * t.element_size() for t in one) + m * n * 2
+        nsets = max(3, int(2.4 * L2_BYTES // per_set) + 1)
+        sets = [one] + [tuple(t.clone() for t in one) for _ in range(nsets - 1)]
+        us = graph_time_us(lambda i: ops.dense_layer_gemm_i4_fp16(*sets[i % nsets]), nsets, launches=nsets if m <= 256 else 8,
+                           reps=15, dev=dev)
+        op, alg = 2.0 * m * n * k, algorithmic_bytes(m, n, k)
+        t_hbm, t_tc = alg / (hbm * 1e9), op / (tc * 1e12)
+        rec = {"M": m, "us": round(us, 2), "TOPS": round(op / us * 1e-6, 1), "bound": "hbm" if t_hbm >= t_tc else "tensor",
+               "frac": round(max(t_hbm, t_tc) * 1e6 / us, 3),
+               "vs_published_rtx4090": round(op / us * 1e-6 / PUBLISHED_TOPS[m], 2) if m in PUBLISHED_TOPS else None}
+        out.append(rec)
+        del sets
+        torch.cuda.empty_cache()
+    return {"shape": f"N={n} K={k}", "peaks": {"hbm_gbs": hbm, "int8_tensor_tops": tc, "int8_peak_is": "2 x measured bf16 cuBLAS burst"},
+            "points": out}
+
+
+def tp_decode_layer(rank, world, dev, hidden=8192, inter=22016, heads=64, batch=32, kvlen=1024, page=32, layers=80, iters=20):
+    """BASELINE config #5: decode step of a Llama-65B-shaped W4A4 layer, tensor-parallel over `world` ranks: heads and MLP
+    channels sharded, hidden state replicated, ONE all-reduce per column->row pair (two per layer), all captured in one
+    CUDA graph per step.  Enough independent layer copies are chained that a rank's weights + KV exceed L2."""
+    import torch.distributed as dist
+    from atom_b200.kvcache import BatchedKvCacheInt4, KvCacheInt4, KvPoolInt4
+    from atom_b200.llama import LlamaConfig
+    from atom_b200.tp import TPLlamaDecoderLayer
+    cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads, num_hidden_layers=1)
+    lh = heads // world
+    w_bytes = (4 * hidden * hidden + 3 * hidden * inter) / 2 * 1.0625 / world
+    kv_bytes = batch * lh * (kvlen + 1) * 136
+    copies = max(2, int(2.4 * L2_BYTES // (w_bytes + kv_bytes)) + 1)
+    mods, kvs = [], []
+    for i in range(copies):
+        mods.append(TPLlamaDecoderLayer(cfg, 0, rank, world).to(dev).init_random(i))
+        pool = KvPoolInt4(1, lh, 128, capacity=batch * ((kvlen + page) // page + 1), block_len=page, device=dev)
+        pool.buf.random_(0, 256); pool.param[..., 0].uniform_(0.01, 0.05); pool.param[..., 1].uniform_(0.0, 0.4)
+        caches = [KvCacheInt4(pool, kvlen) for _ in range(batch)]
+        for c in caches:
+            c.acquire_one()
+        kvs.append(BatchedKvCacheInt4(caches))
+    x = torch.randn(batch, hidden, device=dev, dtype=torch.float16)
+
+    def step():
+        y = x
+        for l, kv in zip(mods, kvs):
+            y = l(y, kv)
+        return y
+
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            step()
+        st.synchronize()
+        if world > 1:
+            dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            step()
+        for _ in range(3):
+            g.replay()
+        st.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(iters):
+            g.replay()
+        e1.record(st)
+        e1.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / iters / copies
+    t = torch.tensor([us], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    us = t.item()
+    rec = {"metric": "llama_decode_tokens_per_s", "model_shape": {"hidden": hidden, "intermediate": inter, "heads": heads, "layers": layers},
+           "tp": world, "batch": batch, "kv_len": kvlen, "us_per_layer": round(us, 1),
+           "value": round(batch / (us * layers * 1e-6), 1), "unit": "tokens/s", "scaling": "strong",
+           "allreduces_per_layer": 2 if world > 1 else 0,
+           "allreduce_bytes": batch * hidden * 2 if world > 1 else 0,
+           "launch": f"one CUDA graph per step over {copies} chained layer copies ({(w_bytes + kv_bytes) * copies / 1e6:.0f} MB of weights + KV per rank > L2), "
+                     "collectives captured inside, device time, max over ranks",
+           "hbm_bytes_per_layer_per_rank": int(w_bytes + kv_bytes),
+           "hbm_frac": round((w_bytes + kv_bytes) / (us * 1e-6) * 1e-9 / 6573.2, 3)}
+    g = None                 # a captured NCCL graph must be gone before the communicator is torn down
+    del mods, kvs
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -115,6 +244,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--m", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-tp", action="store_true")
     a = ap.parse_args()
     M, N, K = a.m, 4096, 4096
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -287,16 +418,34 @@ def main():
     assert ms_per_step * 1e3 / R_sets <= e2e_us_per_step * 1.05, \
         f"timing contract broken: {ms_per_step * 1e3 / R_sets:.2f} us per launch (events) > {e2e_us_per_step:.2f} us per e2e step"
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    # ------------------------------------------------------------------ roofline of the dominant kernel
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
+    # ------------------------------------------------------------------ config #5: tensor-parallel decode layer (all ranks)
+    tp_rec = None
+    if not ref_mode and not a.no_tp:
+        graph = e2e_graphs = None          # the captured graphs reference the operand sets freed next
+        del sets, outs
+        torch.cuda.empty_cache()
+        try:
+            tp_rec = tp_decode_layer(rank, world, dev)
+        except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+            tp_rec = {"error": str(e)[:300]}
+    if rank != 0:
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+        return
+    sweep = None
+    if not ref_mode and not a.no_sweep:
+        try:
+            sweep = gemm_sweep(dev, peaks)
+        except Exception as e:  # noqa: BLE001
+            sweep = {"error": str(e)[:300]}
+    # ------------------------------------------------------------------ roofline of the dominant kernel
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     us_per_launch = ms_per_step * 1e3 / R_sets
@@ -321,13 +470,14 @@ def main():
         "config": {"workload": f"gemm_i4_o16 M={M} N={N} K={K} (K incl. 128 INT8 keeper) group_size=128", "gemms_per_step": R_sets,
                    "l2": f"{R_sets} distinct operand sets per step = {R_sets * per_set / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
                    "launch": "one CUDA graph replay per step" if graph is not None else "python loop on the legacy stream (reference launcher)",
-                   "parallelism": f"dp{world} (independent GEMM problems per rank, no collective)",
+                   "parallelism": f"dp{world} for the GEMM line (independent GEMM problems per rank, no collective); "
+                                  f"tp{world} with two all-reduces per layer for the `tp` record",
                    "published_baseline": (f"{PUBLISHED_TOPS[M]} TOP/s on one RTX 4090 (BASELINE.md section 1, bench_gemm.png)"
                                           if M in PUBLISHED_TOPS else None)},
         "e2e": {"value": e2e_tops, "unit": "TOP/s", "h2d_bytes_per_step": act_bytes, "d2h_bytes_per_step": M * N * 2,
                 "steps": e2e_steps, "note": "one GEMM per step: pinned H2D of the activation tuple, op, D2H of D, stream sync" + ("" if ref_mode else "; the three nodes replayed from one CUDA graph")},
         "gpu_launches": a.steps * R_sets + e2e_steps + 5,
-        "roofline": roof, "clocks": clocks,
+        "roofline": roof, "clocks": clocks, "sweep": sweep, "tp": tp_rec,
     }
     if ref_mode:
         line["cpu_baseline"] = {"value": value, "unit": "TOP/s", "cores": 0, "kind": "reference",
@@ -336,9 +486,11 @@ def main():
         line["gpu_launches"] = 0   # none of OUR kernels ran in this arm
     elif world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(M, N, K)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)          # captured NCCL work + communicator teardown can block: leave once every rank is here
 
 
 if __name__ == "__main__":

@@ -90,6 +90,27 @@ ATOM_API int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, 
                     const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d,
                     void* d_scale, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream);
 
+/* EXTENSION (launch-count reduction): the q, k and v projections of LlamaAttention
+ * (punica/models/llama.py:146-156: dense_layer_gemm_i4_fp16 for q, dense_layer_gemm_i4_o4 for k and v, same input) as ONE
+ * launch over row-concatenated weights  b_qkv u8 [3H,(K-128)/2], b_scale_qkv f16 [K/128-1, 3H], b_keeper_qkv i8 [3H,128],
+ * b_keeper_scale_qkv f16 [3H]  (rows [0,H) = q, [H,2H) = k, [2H,3H) = v).  Outputs are bit-identical to the three separate
+ * calls: q f16 [M,H]; k, v u8 [M,H/2] with k_scale, v_scale f16 [M,H/128,2].  M <= 64: one decode-kernel launch whose
+ * channel tile selects the epilogue; larger M: three launches on the row slices. */
+ATOM_API int atom_gemm_i4_qkv(const void* a, const void* b_qkv, const void* a_scale, const void* b_scale_qkv, const void* a_keeper,
+                     const void* b_keeper_qkv, const void* a_keeper_scale, const void* b_keeper_scale_qkv, void* q, void* k,
+                     void* k_scale, void* v, void* v_scale, int64_t M, int64_t H, int64_t K, uint32_t flags, void* stream);
+
+/* EXTENSION (launch-count reduction): LlamaMLP's gate_proj, up_proj and activate_fp16_i4
+ * (punica/models/llama.py:85-87) as ONE launch for decode batches (M <= 64; ATOM_E_UNSUPPORTED above): weights
+ * row-concatenated  b_gu u8 [2I,(K-128)/2] (rows [0,I) = gate, [I,2I) = up), b_scale_gu f16 [K/128-1, 2I], b_keeper_gu
+ * i8 [2I,128], b_keeper_scale_gu f16 [2I].  Outputs: the activation 4-tuple of activate_fp16_i4(gate, up) -- o_outliers i8
+ * [M,128], o_norms u8 [M,(I-128)/2], outlier_scales f16 [scale_size(M)], norm_scales f16 [I/128-1, scale_size(M)] --
+ * bit-identical to the three separate calls (both projections are rounded to FP16 before the activation, as there). */
+ATOM_API int atom_gemm_i4_gateup_act(const void* a, const void* b_gu, const void* a_scale, const void* b_scale_gu, const void* a_keeper,
+                            const void* b_keeper_gu, const void* a_keeper_scale, const void* b_keeper_scale_gu, void* o_outliers,
+                            void* o_norms, void* outlier_scales, void* norm_scales, int64_t M, int64_t I, int64_t K, uint32_t flags,
+                            void* stream);
+
 /* Debug aid (no reference counterpart): when non-NULL, every GEMM CTA writes 128 clock64() stamps of its pipeline
  * stages to device_buffer[cta*128 ...] (layout in gemm_i4_sm100.cuh).  NULL switches tracing off. */
 ATOM_API int atom_gemm_set_trace(void* device_buffer);

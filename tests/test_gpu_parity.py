@@ -212,3 +212,47 @@ def test_errors_are_loud():
         ops.dense_layer_gemm_i4_fp16(*t)
     with pytest.raises(RuntimeError):
         ops.reorder_fp16_i4(torch.zeros(4, 4096, dtype=torch.float16), torch.zeros(4096, dtype=torch.int16))  # CPU tensors
+
+
+def _concat_weights(parts):
+    """Row-concatenate LinearInt4-style operand tuples (b, b_scale [G, N], b_keeper, b_keeper_scale) of equal K."""
+    b = np.concatenate([p[0] for p in parts], 0)
+    bs = np.concatenate([p[1] for p in parts], 1)
+    bk = np.concatenate([p[2] for p in parts], 0)
+    bks = np.concatenate([p[3] for p in parts], 0)
+    return b, bs, bk, bks
+
+
+@pytest.mark.parametrize("m,h,k", [(16, 256, 512), (7, 384, 1024), (32, 512, 2048), (48, 128, 512), (16, 4096, 4096), (100, 256, 1024)])
+def test_fused_qkv_equals_three_projections(m, h, k):
+    """EXTENSION op: one launch for q (fp16) + k, v (o4) must reproduce the three operator calls bit for bit."""
+    from atom_b200 import ops
+    t = [O.make_gemm_inputs(m, h, k, seed=m + h + k + i) for i in range(3)]
+    act = [T(t[0][i]) for i in (0, 2, 4, 6)]                      # a, a_scale, a_keeper, a_keeper_scale of the first set
+    ws = [(x[1], x[3], x[5], x[7]) for x in t]
+    q_ref = ops.dense_layer_gemm_i4_fp16(act[0], T(ws[0][0]), act[1], T(ws[0][1]), act[2], T(ws[0][2]), act[3], T(ws[0][3]), flags=1)
+    k_ref = ops.dense_layer_gemm_i4_o4(act[0], T(ws[1][0]), act[1], T(ws[1][1]), act[2], T(ws[1][2]), act[3], T(ws[1][3]))
+    v_ref = ops.dense_layer_gemm_i4_o4(act[0], T(ws[2][0]), act[1], T(ws[2][1]), act[2], T(ws[2][2]), act[3], T(ws[2][3]))
+    b, bs, bk, bks = _concat_weights(ws)
+    q, (kk, ks), (vv, vs) = ops.dense_layer_gemm_i4_qkv(act[0], T(b), act[1], T(bs), act[2], T(bk), act[3], T(bks))
+    assert torch.equal(q, q_ref)
+    assert torch.equal(kk, k_ref[0]) and torch.equal(ks, k_ref[1])
+    assert torch.equal(vv, v_ref[0]) and torch.equal(vs, v_ref[1])
+
+
+@pytest.mark.parametrize("m,inter,k", [(16, 256, 512), (5, 384, 1024), (32, 512, 1024), (64, 256, 512), (16, 11008, 4096)])
+def test_fused_gateup_activation_equals_three_calls(m, inter, k):
+    """EXTENSION op: gate_proj + up_proj + activate_fp16_i4 in one launch: the activation 4-tuple must be bit-identical."""
+    from atom_b200 import ops
+    t = [O.make_gemm_inputs(m, inter, k, seed=3 * m + inter + k + i) for i in range(2)]
+    act = [T(t[0][i]) for i in (0, 2, 4, 6)]
+    ws = [(x[1], x[3], x[5], x[7]) for x in t]
+    g = ops.dense_layer_gemm_i4_fp16(act[0], T(ws[0][0]), act[1], T(ws[0][1]), act[2], T(ws[0][2]), act[3], T(ws[0][3]), flags=1)
+    u = ops.dense_layer_gemm_i4_fp16(act[0], T(ws[1][0]), act[1], T(ws[1][1]), act[2], T(ws[1][2]), act[3], T(ws[1][3]), flags=1)
+    ref = ops.activate_fp16_i4(g, u)
+    b, bs, bk, bks = _concat_weights(ws)
+    got = ops.dense_layer_gemm_i4_gateup_act(act[0], T(b), act[1], T(bs), act[2], T(bk), act[3], T(bks))
+    assert torch.equal(got[0], ref[0]), "INT8 outliers differ"
+    assert torch.equal(got[1], ref[1]), "packed INT4 differs"
+    sel = torch.tensor([O.scale_index(r) + 2 * j for r in range(m) for j in range(4)], device="cuda:0")
+    assert torch.equal(got[2][sel], ref[2][sel]) and torch.equal(got[3][:, sel], ref[3][:, sel]), "scales differ"

@@ -23,7 +23,7 @@ for s in $STEPS; do case $s in
   micro)   echo "== microbenchmarks"; for b in microbench sync_bench tma_bench tmem_bench; do timeout 120 ./tools/$b > $OUT/$b.jsonl 2>&1; echo "$b rc=$?"; done ;;
   sk)      echo "== skinny GEMM: probes, parity, timing (PDL on / off, legacy kernel beside it)"
            timeout 300 python tools/gpu_check.py diag 2>&1 | tee $OUT/sk_diag.jsonl | cut -c1-400
-           timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py -m gpu -q -x --timeout=300 -p no:cacheprovider -k "gemm" > $OUT/pytest_sk.txt 2>&1; echo "rc=$?"; tail -12 $OUT/pytest_sk.txt
+           timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py -m gpu -q -x --timeout=300 -p no:cacheprovider -k "gemm or fused" > $OUT/pytest_sk.txt 2>&1; echo "rc=$?"; tail -12 $OUT/pytest_sk.txt
            timeout 300 python tools/gpu_check.py gtime 16 32 64 2> $OUT/sk_gtime.err | tee $OUT/sk_gtime.jsonl; tail -3 $OUT/sk_gtime.err
            ATOM_B200_GEMM_PDL=0 timeout 300 python tools/gpu_check.py gtime 16 2>> $OUT/sk_gtime.err | tee $OUT/sk_gtime_nopdl.jsonl
            timeout 300 python tools/gpu_check.py gshape 2>> $OUT/sk_gtime.err | tee $OUT/sk_gshape.jsonl
