@@ -21,6 +21,7 @@
 #include "gemm_i4_skinny_sm100.cuh"
 #include "gemm_i4_tall_sm100.cuh"
 #include "kv_kernels.cuh"
+#include "prefill_kernels.cuh"
 #include "quant_kernels.cuh"
 
 namespace {
@@ -545,6 +546,29 @@ int atom_gemm_i4_o4(const void* a, const void* b, const void* a_scale, const voi
                     void* d_scale, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream) {
   return gemm_common(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, d, d_scale, M, N, K,
                      flags, stream, true);
+}
+
+int atom_prefill_attention_i4(const void* q, const void* k, const void* k_param, const void* v, const void* v_param,
+                              const void* seqlen_indptr, const void* pos_of_token, const void* rope_table, void* k_f16, void* v_f16,
+                              void* out, int total_tokens, int batch_size, int max_len, int num_heads, void* stream) {
+  ATOM_REQUIRE(q && k && k_param && v && v_param && seqlen_indptr && pos_of_token && rope_table && k_f16 && v_f16 && out,
+               "prefill_attention_i4: null pointer argument");
+  ATOM_REQUIRE(batch_size > 0 && num_heads > 0 && max_len > 0, "prefill_attention_i4: batch_size=%d num_heads=%d max_len=%d must be positive",
+               batch_size, num_heads, max_len);
+  ATOM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(k_f16) && aligned16(v_f16) && aligned16(out),
+               "prefill_attention_i4: pointers must be 16-byte aligned");
+  if (total_tokens <= 0) return ATOM_OK;
+  const long long th = (long long)total_tokens * num_heads;
+  atom::kv_dequant_rope_kernel<<<(unsigned)((th + 3) / 4), 256, 0, (cudaStream_t)stream>>>(
+      (const uint8_t*)k, (const __half2*)k_param, (const uint8_t*)v, (const __half2*)v_param, (const int32_t*)pos_of_token,
+      (const float2*)rope_table, (__half*)k_f16, (__half*)v_f16, th, num_heads);
+  int rc = check_launch("prefill_attention_i4 (dequant + RoPE)");
+  if (rc) return rc;
+  const dim3 grid((unsigned)((max_len + atom::PF_BQ - 1) / atom::PF_BQ), (unsigned)batch_size, (unsigned)num_heads);
+  atom::prefill_attn_kernel<<<grid, atom::PF_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __half*)q, (const __half*)k_f16, (const __half*)v_f16, (const int32_t*)seqlen_indptr, (const float2*)rope_table,
+      (__half*)out, num_heads, 0.08838834764831845f * 1.4426950408889634f);
+  return check_launch("prefill_attention_i4");
 }
 
 static int kv_check(const char* what, const void* data, const void* param, const void* indptr, const void* indices,

@@ -217,19 +217,10 @@ class LlamaAttention(nn.Module):
                            k_proj[1][:blen.doff].view(-1, nh, hd // 128 * 2), v_proj[1][:blen.doff].view(-1, nh, hd // 128 * 2),
                            blen.indptr, self.layer_idx)
             nvtx.range_pop()
-            kd = _dequant_o4(k_proj[0][:blen.doff], k_proj[1][:blen.doff], nh)
-            vd = _dequant_o4(v_proj[0][:blen.doff], v_proj[1][:blen.doff], nh)
-            off = 0
-            for q_len in blen.prefills:
-                nvtx.range_push("sdpa")
-                q = q_proj[off:off + q_len].view(1, q_len, nh, hd).transpose(1, 2)
-                k = kd[off:off + q_len].view(1, q_len, nh, hd).transpose(1, 2)
-                v = vd[off:off + q_len].view(1, q_len, nh, hd).transpose(1, 2)
-                q, k = rotary_pos_emb(q, k, 0)
-                o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)
-                stack.append(o.squeeze(0).transpose(0, 1).reshape(q_len, self.hidden_size))
-                off += q_len
-                nvtx.range_pop()
+            nvtx.range_push("prefill_attention")
+            stack.append(ops.prefill_attention_i4(q_proj[:blen.doff], k_proj[0][:blen.doff], k_proj[1][:blen.doff],
+                                                  v_proj[0][:blen.doff], v_proj[1][:blen.doff], blen.indptr, seqlens=list(blen.prefills)))
+            nvtx.range_pop()
         if blen.decode > 0:
             q = q_proj[blen.doff:].view(blen.decode, nh, hd)
             k = k_proj[0][blen.doff:].view(blen.decode, nh, hd // 2)

@@ -229,6 +229,50 @@ def batch_decode_i4(q, kv, layer_idx):
     return o
 
 
+_rope_tables = {}
+
+
+def rope_table(max_len, device):
+    """(cos, sin)(pos * theta_i) for pos < max_len, i < 64, theta_i = 1e4^(-i/64), float32 [max_len, 64, 2] -- the factors of
+    punica/models/llama.py:18-32 (`rotary_pos_emb`), computed the same way and cached per device."""
+    size = max(256, 1 << (int(max_len) - 1).bit_length())
+    key = (str(device), size)
+    t = _rope_tables.get(key)
+    if t is None:
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, 128, 2, device=device).float() / 128))
+        freqs = torch.einsum("i,j->ij", torch.arange(0, size, device=device, dtype=torch.float32), inv_freq)
+        t = torch.stack((freqs.cos(), freqs.sin()), dim=-1).contiguous()
+        _rope_tables[key] = t
+    return t
+
+
+def prefill_attention_i4(q, k, k_param, v, v_param, seqlen_indptr, seqlens=None):
+    """EXTENSION: causal prefill attention of every prompt over its own quantised K/V (the o4 projection outputs) with RoPE,
+    one launch for all prompts and heads.  q f16 [T, H*128]; k, v u8 [T, H*64]; k_param, v_param f16 [T, H*2];
+    seqlen_indptr i32 [B+1] (device); seqlens: the prompt lengths as host ints (avoids a device read).  Returns f16 [T, H*128]."""
+    _req_width("prefill_attention_i4", f16_q_2=q, k_1=k, f16_k_param_2=k_param, v_1=v, f16_v_param_2=v_param)
+    _req_cuda(q, k, k_param, v, v_param, seqlen_indptr)
+    t, hd = q.shape
+    h = hd // 128
+    if hd % 128 or k.shape != (t, h * 64) or v.shape != k.shape or k_param.numel() != t * h * 2 or v_param.numel() != t * h * 2:
+        raise RuntimeError("prefill_attention_i4: shape mismatch (head_dim must be 128)")
+    if seqlens is None:
+        ip = seqlen_indptr.cpu()
+        seqlens = (ip[1:] - ip[:-1]).tolist()
+    b, max_len = len(seqlens), max(seqlens)
+    if sum(seqlens) != t or seqlen_indptr.numel() != b + 1:
+        raise RuntimeError("prefill_attention_i4: seqlen_indptr does not cover the tokens")
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in seqlens]).to(q.device, non_blocking=True)
+    table = rope_table(max_len, q.device)
+    kf, vf, out = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.lib().atom_prefill_attention_i4(q.data_ptr(), k.data_ptr(), k_param.data_ptr(), v.data_ptr(), v_param.data_ptr(),
+                                                        seqlen_indptr.data_ptr(), pos.data_ptr(), table.data_ptr(), kf.data_ptr(),
+                                                        vf.data_ptr(), out.data_ptr(), t, b, max_len, h, _stream(q)),
+                   "prefill_attention_i4")
+    return out
+
+
 def init_kv_i4(kv, k, v, k_param, v_param, seqlen_indptr, layer_idx):
     """ops/__init__.py:35-46"""
     _req_cuda(kv.data, kv.param, kv.indptr, kv.indicies, kv.last_page_offset, k, v, k_param, v_param, seqlen_indptr)

@@ -128,6 +128,17 @@ ATOM_API int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, c
                          const void* kv_indices, const void* last_page_offset, int num_layers, int layer_idx,
                          int num_heads, int page_size, int batch_size, void* stream);
 
+/* EXTENSION: the prefill attention the reference leaves as a placeholder
+ * (punica/models/llama.py:171-190, SDPA over torch.randn K/V): causal attention of every prompt over its own just-quantised
+ * K/V -- the o4 outputs of the k/v projections, x = nibble * scale - zero (quantization.cuh:76) -- with RoPE(theta 1e4) on q
+ * and k at positions 0..len-1, head_dim 128.
+ *   q f16 [T, H*128]; k, v u8 [T, H*64]; k_param, v_param f16 [T, H, 2]; seqlen_indptr i32 [B+1]; pos_of_token i32 [T];
+ *   rope_table f32 [max_len, 64, 2] = (cos, sin)(pos * 1e4^(-i/64)); k_f16, v_f16 f16 [T, H*128] scratch (caller-owned,
+ *   holds RoPE(dequant k) and dequant v afterwards); out f16 [T, H*128].  max_len >= the longest prompt. */
+ATOM_API int atom_prefill_attention_i4(const void* q, const void* k, const void* k_param, const void* v, const void* v_param,
+                              const void* seqlen_indptr, const void* pos_of_token, const void* rope_table, void* k_f16, void* v_f16,
+                              void* out, int total_tokens, int batch_size, int max_len, int num_heads, void* stream);
+
 /* replaces append_kv_i4 (punica_ops.cc:166-209 -> FlashInferAppendKvKernel_i4<128>, flashinfer_impl.cuh:73-96)
  *   k,v u8 [B,H,64]  k_param,v_param f16 [B,H,2] */
 ATOM_API int atom_append_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,

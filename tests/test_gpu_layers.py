@@ -110,3 +110,34 @@ def test_decode_step_is_cuda_graph_capturable():
             y = layer(x, blen, None, kv)
         g.replay(); st.synchronize()
     assert torch.equal(y, eager)
+
+
+@pytest.mark.parametrize("lens,heads", [([5], 2), ([64, 1, 130], 4), ([300, 77], 3), ([2048], 2)])
+def test_prefill_attention_matches_the_eager_dequant_rope_sdpa_path(lens, heads):
+    """EXTENSION op: one-launch causal prefill attention over the just-quantised K/V vs the eager pipeline
+    round 1 shipped (torch dequantisation, rotary_pos_emb of llama.py:18-32, scaled_dot_product_attention per prompt)."""
+    from atom_b200 import ops
+    from atom_b200.llama import _dequant_o4, rotary_pos_emb
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(sum(lens) + heads)
+    t = sum(lens)
+    q = (torch.randn(t, heads * 128, generator=g) * 1.5).half().to(dev)
+    k4 = torch.randint(0, 256, (t, heads * 64), dtype=torch.uint8, generator=g).to(dev)
+    v4 = torch.randint(0, 256, (t, heads * 64), dtype=torch.uint8, generator=g).to(dev)
+    kp = torch.stack((torch.rand(t, heads, generator=g) * 0.2 + 0.05, torch.rand(t, heads, generator=g) * 1.5), -1).half().to(dev).view(t, heads * 2)
+    vp = torch.stack((torch.rand(t, heads, generator=g) * 0.2 + 0.05, torch.rand(t, heads, generator=g) * 1.5), -1).half().to(dev).view(t, heads * 2)
+    indptr = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=dev)
+    got = ops.prefill_attention_i4(q, k4, kp, v4, vp, indptr, seqlens=lens)
+    kd, vd = _dequant_o4(k4, kp, heads), _dequant_o4(v4, vp, heads)
+    ref, off = [], 0
+    for n in lens:
+        qq = q[off:off + n].view(1, n, heads, 128).transpose(1, 2)
+        kk = kd[off:off + n].view(1, n, heads, 128).transpose(1, 2)
+        vv = vd[off:off + n].view(1, n, heads, 128).transpose(1, 2)
+        qq, kk = rotary_pos_emb(qq, kk, 0)
+        o = torch.nn.functional.scaled_dot_product_attention(qq.float(), kk.float(), vv.float(), is_causal=True)
+        ref.append(o.squeeze(0).transpose(0, 1).reshape(n, heads * 128))
+        off += n
+    ref = torch.cat(ref, 0)
+    err = (got.float() - ref).abs() - 5e-3 * ref.abs()
+    assert err.max().item() <= 5e-3, f"worst excess over rtol*|ref| = {err.max().item():.2e}"
