@@ -22,6 +22,7 @@
 #include "gemm_i4_tall_sm100.cuh"
 #include "kv_kernels.cuh"
 #include "prefill_kernels.cuh"
+#include "comm_kernels.cuh"
 #include "quant_kernels.cuh"
 
 namespace {
@@ -569,6 +570,19 @@ int atom_prefill_attention_i4(const void* q, const void* k, const void* k_param,
       (const __half*)q, (const __half*)k_f16, (const __half*)v_f16, (const int32_t*)seqlen_indptr, (const float2*)rope_table,
       (__half*)out, num_heads, 0.08838834764831845f * 1.4426950408889634f);
   return check_launch("prefill_attention_i4");
+}
+
+int atom_allreduce_push_f16(const void* in, void* out, const void* peer_buffers, const void* peer_flags, void* epoch,
+                            int64_t numel, int64_t slot_elems, int rank, int world, void* stream) {
+  ATOM_REQUIRE(in && out && peer_buffers && peer_flags && epoch, "allreduce_push_f16: null pointer argument");
+  ATOM_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "allreduce_push_f16: rank=%d world=%d", rank, world);
+  ATOM_REQUIRE(numel > 0 && numel % 8 == 0 && numel <= slot_elems && slot_elems % 8 == 0,
+               "allreduce_push_f16: numel=%lld must be a positive multiple of 8 and fit a slot of %lld elements", (long long)numel, (long long)slot_elems);
+  ATOM_REQUIRE(aligned16(in) && aligned16(out), "allreduce_push_f16: in / out must be 16-byte aligned");
+  atom::allreduce_push_kernel<<<atom::AR_CTAS, atom::AR_THREADS, 0, (cudaStream_t)stream>>>(
+      (const uint4*)in, (uint4*)out, (uint4* const*)peer_buffers, (uint32_t* const*)peer_flags, (uint32_t*)epoch, numel / 8,
+      slot_elems / 8, rank, world);
+  return check_launch("allreduce_push_f16");
 }
 
 static int kv_check(const char* what, const void* data, const void* param, const void* indptr, const void* indices,

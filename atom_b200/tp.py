@@ -15,7 +15,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import ops
-from .llama import LinearInt4
+from .llama import LinearInt4, fuse_linear_rows
 
 
 def split_sizes(total: int, world: int, quantum: int = 128, minimum: int = 256) -> List[int]:
@@ -60,21 +60,26 @@ class ColumnParallelLinearInt4(LinearInt4):
 class RowParallelLinearInt4(nn.Module):
     """Input channels [k0, k1) of a linear layer as a self-contained W4A4 operand + all-reduce of the partial outputs."""
 
-    def __init__(self, in_features, out_features, rank, world, group: Optional[dist.ProcessGroup] = None, gemm_fn=None):
+    def __init__(self, in_features, out_features, rank, world, group: Optional[dist.ProcessGroup] = None, gemm_fn=None,
+                 allreduce=None):
         super().__init__()
         self.sizes = split_sizes(in_features, world)
         self.k0, self.k1 = slice_range(self.sizes, rank)
         self.local = LinearInt4(self.k1 - self.k0, out_features, out_dtype="fp16")
         self.world, self.group = world, group
         self.gemm_fn = gemm_fn
+        self.allreduce = allreduce       # comm.PushAllReduce / NcclAllReduce; None = plain dist.all_reduce
 
     def forward(self, local_tuple):
         outlier, norms, outlier_scales, norm_scales = local_tuple
         f = self.gemm_fn or ops.dense_layer_gemm_i4_fp16
         y = f(norms, self.local.weight_int4, norm_scales, self.local.scale_int4, outlier, self.local.weight_int8,
               outlier_scales, self.local.scale_int8)
-        if self.world > 1:
-            dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)   # the one collective of the column->row pair
+        if self.world > 1:                   # the one collective of the column->row pair
+            if self.allreduce is not None:
+                y = self.allreduce(y)
+            else:
+                dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
         return y
 
 
@@ -82,7 +87,7 @@ class TPLlamaDecoderLayer(nn.Module):
     """One Llama decoder layer over `world` ranks: heads and MLP channels are sharded, hidden states replicated.
     forward(hidden, decode_kv) runs a decode step (one token per sequence); KV cache pools are per rank (local heads)."""
 
-    def __init__(self, config, layer_idx, rank, world, group=None):
+    def __init__(self, config, layer_idx, rank, world, group=None, allreduce=None):
         super().__init__()
         from .llama import LlamaRMSNormInt4
         h, nh = config.hidden_size, config.num_attention_heads
@@ -94,13 +99,13 @@ class TPLlamaDecoderLayer(nn.Module):
         self.q_proj = LinearInt4(h, hl, "fp16")
         self.k_proj = LinearInt4(h, hl, "int4")
         self.v_proj = LinearInt4(h, hl, "int4")
-        self.o_proj = RowParallelLinearInt4(h, h, rank, world, group)
+        self.o_proj = RowParallelLinearInt4(h, h, rank, world, group, allreduce=allreduce)
         assert self.o_proj.k1 - self.o_proj.k0 == hl, "head slices and o_proj K-slices must coincide"
         self.inter_sizes = split_sizes(config.intermediate_size, world)
         il = self.inter_sizes[rank]
         self.gate_proj = LinearInt4(h, il, "fp16")
         self.up_proj = LinearInt4(h, il, "fp16")
-        self.down_proj = RowParallelLinearInt4(config.intermediate_size, h, rank, world, group)
+        self.down_proj = RowParallelLinearInt4(config.intermediate_size, h, rank, world, group, allreduce=allreduce)
         self.input_layernorm = LlamaRMSNormInt4(h, eps=config.rms_norm_eps)
         self.post_attention_layernorm = LlamaRMSNormInt4(h, eps=config.rms_norm_eps)
         self.attn_reorder_index = nn.Parameter(torch.randperm(hl, dtype=torch.int16), requires_grad=False)   # shard-local
@@ -111,18 +116,36 @@ class TPLlamaDecoderLayer(nn.Module):
             if isinstance(m, LinearInt4):
                 m.init_random(seed * 64 + self.rank * 8 + i)
                 i += 1
+        if self.q_proj.weight_int4.is_cuda:
+            self.fuse()
+        return self
+
+    def fuse(self):
+        """Fused decode launches (ops.dense_layer_gemm_i4_qkv / _gateup_act) on this rank's shards."""
+        self._qkv = fuse_linear_rows([self.q_proj, self.k_proj, self.v_proj])
+        self._gu = fuse_linear_rows([self.gate_proj, self.up_proj])
         return self
 
     def forward(self, hidden_states, decode_kv):
         b = hidden_states.shape[0]
         x = self.input_layernorm(hidden_states)
-        q = self.q_proj(x).view(b, self.local_heads, 128)
-        k, ks = self.k_proj(x)
-        v, vs = self.v_proj(x)
+        fused = getattr(self, "_qkv", None) is not None and b <= 64
+        if fused:
+            w4, s4, w8, s8 = self._qkv
+            q, (k, ks), (v, vs) = ops.dense_layer_gemm_i4_qkv(x[1], w4, x[3], s4, x[0], w8, x[2], s8)
+            q = q.view(b, self.local_heads, 128)
+        else:
+            q = self.q_proj(x).view(b, self.local_heads, 128)
+            k, ks = self.k_proj(x)
+            v, vs = self.v_proj(x)
         ops.append_kv_i4(decode_kv, k.view(b, self.local_heads, 64), v.view(b, self.local_heads, 64),
                          ks.view(b, self.local_heads, 2), vs.view(b, self.local_heads, 2), self.layer_idx)
         attn = ops.batch_decode_i4(q, decode_kv, self.layer_idx).view(b, self.local_heads * 128)
-        hidden_states = hidden_states + self.o_proj(ops.reorder_fp16_i4(attn, self.attn_reorder_index))      # all-reduce #1
-        x = self.post_attention_layernorm(hidden_states)
-        act = ops.activate_fp16_i4(self.gate_proj(x), self.up_proj(x))
+        o = self.o_proj(ops.reorder_fp16_i4(attn, self.attn_reorder_index))                                  # all-reduce #1
+        hidden_states, x = self.post_attention_layernorm.forward_add(o, hidden_states)                        # residual add folded into the norm
+        if fused:
+            w4, s4, w8, s8 = self._gu
+            act = ops.dense_layer_gemm_i4_gateup_act(x[1], w4, x[3], s4, x[0], w8, x[2], s8)
+        else:
+            act = ops.activate_fp16_i4(self.gate_proj(x), self.up_proj(x))
         return hidden_states + self.down_proj(act)                                                           # all-reduce #2

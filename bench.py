@@ -171,6 +171,8 @@ def tp_decode_layer(rank, world, dev, hidden=8192, inter=22016, heads=64, batch=
     from atom_b200.kvcache import BatchedKvCacheInt4, KvCacheInt4, KvPoolInt4
     from atom_b200.llama import LlamaConfig
     from atom_b200.tp import TPLlamaDecoderLayer
+    from atom_b200.comm import make_allreduce
+    allreduce = make_allreduce(batch * hidden, dev) if world > 1 else None
     cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads, num_hidden_layers=1)
     lh = heads // world
     w_bytes = (4 * hidden * hidden + 3 * hidden * inter) / 2 * 1.0625 / world
@@ -178,7 +180,7 @@ def tp_decode_layer(rank, world, dev, hidden=8192, inter=22016, heads=64, batch=
     copies = max(2, int(2.4 * L2_BYTES // (w_bytes + kv_bytes)) + 1)
     mods, kvs = [], []
     for i in range(copies):
-        mods.append(TPLlamaDecoderLayer(cfg, 0, rank, world).to(dev).init_random(i))
+        mods.append(TPLlamaDecoderLayer(cfg, 0, rank, world, allreduce=allreduce).to(dev).init_random(i))
         pool = KvPoolInt4(1, lh, 128, capacity=batch * ((kvlen + page) // page + 1), block_len=page, device=dev)
         pool.buf.random_(0, 256); pool.param[..., 0].uniform_(0.01, 0.05); pool.param[..., 1].uniform_(0.0, 0.4)
         caches = [KvCacheInt4(pool, kvlen) for _ in range(batch)]
@@ -223,7 +225,7 @@ def tp_decode_layer(rank, world, dev, hidden=8192, inter=22016, heads=64, batch=
     rec = {"metric": "llama_decode_tokens_per_s", "model_shape": {"hidden": hidden, "intermediate": inter, "heads": heads, "layers": layers},
            "tp": world, "batch": batch, "kv_len": kvlen, "us_per_layer": round(us, 1),
            "value": round(batch / (us * layers * 1e-6), 1), "unit": "tokens/s", "scaling": "strong",
-           "allreduces_per_layer": 2 if world > 1 else 0,
+           "allreduces_per_layer": 2 if world > 1 else 0, "allreduce": allreduce.name if allreduce is not None else None,
            "allreduce_bytes": batch * hidden * 2 if world > 1 else 0,
            "launch": f"one CUDA graph per step over {copies} chained layer copies ({(w_bytes + kv_bytes) * copies / 1e6:.0f} MB of weights + KV per rank > L2), "
                      "collectives captured inside, device time, max over ranks",
