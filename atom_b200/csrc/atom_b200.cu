@@ -20,6 +20,7 @@
 #include "gemm_i4_sm100.cuh"
 #include "gemm_i4_skinny_sm100.cuh"
 #include "gemm_i4_tall_sm100.cuh"
+#include "gemm_i4_wide_sm100.cuh"
 #include "kv_kernels.cuh"
 #include "prefill_kernels.cuh"
 #include "comm_kernels.cuh"
@@ -312,6 +313,37 @@ int launch_tall(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
   return ATOM_OK;
 }
 
+// Prefill-shape kernel with the token operand in tensor memory, 128 x 256 tiles (gemm_i4_wide_sm100.cuh).
+template <bool kO4>
+int launch_wide(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t stream) {
+  using C = atom::WideCfg<kO4>;
+  auto kern = atom::gemm_i4_wide_kernel<kO4>;
+  int rc = ensure_dynamic_smem(kern, C::SMEM_BYTES, "gemm_i4 (wide)");
+  if (rc) return rc;
+  const uint64_t kp = (uint64_t)(op.K - 128) / 2;
+  CUtensorMap ta4, tb4, ta8, tb8;
+  if ((rc = make_map(&ta4, op.a, kp, op.M, kp, 64, C::BM, 2))) return rc;
+  if ((rc = make_map_quadswap(&tb4, op.b, kp, op.N, kp, 64, C::BH, 0))) return rc;
+  if ((rc = make_map(&ta8, op.ak, 128, op.M, 128, 128, C::BM, 1))) return rc;
+  if ((rc = make_map_quadswap(&tb8, op.bk, 128, op.N, 128, 128, C::BH, 1))) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((op.N + C::NH * C::BH - 1) / (C::NH * C::BH)), (unsigned)((op.M + C::BM - 1) / C::BM), 1);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (gemm_pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta4, tb4, ta8, tb8, args);
+  if (e != cudaSuccess) return fail(ATOM_E_CUDA, "gemm_i4 (wide) launch: %s", cudaGetErrorString(e));
+  return ATOM_OK;
+}
+
 template <bool kO4>
 int skinny_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   constexpr int kEpi = kO4 ? atom::EPI_O4 : atom::EPI_O16;
@@ -347,8 +379,13 @@ template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
   // <swap, BN, groups per pipeline stage, packed stages, K split, o4, converter warps, epilogue warpgroups>
-  if (!skinny) return (flags & ATOM_GEMM_LEGACY_TALL) ? launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream)
-                                                      : launch_tall<kO4>(op, args, stream);
+  if (!skinny) {
+    if (flags & ATOM_GEMM_LEGACY_TALL) return launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream);
+    // 128 x 256 tiles (token operand in tensor memory) once they fill the machine, 128 x 128 tiles below
+    const int64_t wide_tiles = ((op.M + 127) / 128) * ((op.N + 255) / 256);
+    const bool wide = (flags & ATOM_GEMM_FORCE_WIDE) || (!(flags & ATOM_GEMM_NO_WIDE) && wide_tiles >= 120);
+    return wide ? launch_wide<kO4>(op, args, stream) : launch_tall<kO4>(op, args, stream);
+  }
   if (op.M <= 64 && !(flags & ATOM_GEMM_LEGACY_SKINNY)) return skinny_dispatch<kO4>(op, args, flags, stream);
   // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not
   // cover the machine (the kernel is HBM-bound on the weights: more CTAs = more bytes in flight)

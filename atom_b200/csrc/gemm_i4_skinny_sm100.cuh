@@ -162,8 +162,10 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   const int iters = g_end - g_begin;                                  // groups of this CTA, the keeper (if any) last
   const int n4 = max(0, min(g_end, args.G) - g_begin);                // ... of which INT4
   const bool has_keeper = n4 < iters;
-  const int np4 = (n4 + 1) >> 1;                                      // INT4 units (pairs; the last may be single)
-  const int nu = np4 + (has_keeper ? 1 : 0);                          // units: INT4 pairs, then the keeper on its own
+  // A unit = two consecutive groups of this CTA (the last unit may hold one); the keeper, always the CTA's last group, shares
+  // a unit with the last INT4 group when their count is odd, so the rank that owns the keeper does not run an extra unit.
+  const int np4 = (n4 + 1) >> 1;                                      // units that contain INT4 groups
+  const int nu = (iters + 1) >> 1;
   if (threadIdx.x == 0) { griddep_launch_dependents(); trace_stamp(args, 0); }
 
   // ---------------------------------------------------------------- setup
@@ -224,41 +226,34 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     // uniform), ONE elected lane issues the tcgen05 instructions; one commit per pair
     constexpr uint32_t idesc = umma_idesc_i8(C::BM, BN);
     for (int u = 0; u < nu; ++u) {
-      const int as = u % C::ACC_PAIRS;
+      const int as = u % C::ACC_PAIRS, ar = u % C::A_PAIRS, b = u >> 1;           // QB = 4 groups = 2 units per token batch
+      const int ng = min(2, iters - 2 * u), ng4 = max(0, min(2, n4 - 2 * u));    // groups of the unit, of which INT4
       if (u >= C::ACC_PAIRS) mbar_wait(&acc_empty[as], ((u / C::ACC_PAIRS) - 1) & 1);
       const uint32_t d0 = tmem_base + C::ACC_COL0 + as * 2 * BN;
-      if (u < np4) {
-        const int ar = u % C::A_PAIRS, ng = min(2, n4 - 2 * u), b = u >> 1;     // QB = 4 groups = 2 pairs per batch
+      if (ng4 > 0) {
         if ((u & 1) == 0) mbar_wait(&qx_full[b & 1], (b >> 1) & 1);
         mbar_wait(&a_full[ar], (u / C::A_PAIRS) & 1);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          if (u < 8) trace_stamp(args, 88 + u);
-          for (int j = 0; j < ng; ++j) {
-            const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + ((2 * u + j) % C::QS) * C::EXP_Q));
+      }
+      if (ng > ng4) { mbar_wait(keep_full, 0); mbar_wait(kq_full, 0); }
+      tc_fence_after();
+      if (elect_one_sync()) {
+        if (u < 8) trace_stamp(args, 88 + u);
+        for (int j = 0; j < ng4; ++j) {
+          const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_EXP_Q + ((2 * u + j) % C::QS) * C::EXP_Q));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)      // 4 x K=32: 8 tensor-memory columns of A, 32 B of each token row
-              umma_i8_ts(d0 + j * BN, tmem_base + C::A_COL0 + ar * 64 + j * 32 + k * 8, dq + (uint64_t)(k * 2), idesc, k > 0);
-          }
-          if (u < 8) trace_stamp(args, 16 + u);
-          if ((u & 1) == 1 || u == np4 - 1) umma_commit(&q_empty[b & 1]);    // the batch's token tiles are consumed
-          umma_commit(&mma_done[ar]);          // accumulators ready AND operand slot reusable
-          if (u < 8) trace_stamp(args, 32 + u);
+          for (int k = 0; k < 4; ++k)      // 4 x K=32: 8 tensor-memory columns of A, 32 B of each token row
+            umma_i8_ts(d0 + j * BN, tmem_base + C::A_COL0 + ar * 64 + j * 32 + k * 8, dq + (uint64_t)(k * 2), idesc, k > 0);
         }
-      } else {
-        mbar_wait(keep_full, 0);
-        mbar_wait(kq_full, 0);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          if (u < 8) trace_stamp(args, 88 + u);
+        if (ng > ng4) {                    // the INT8 keeper group: both operands from shared memory
           const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + C::OFF_KEEP_P));
           const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_KEEP_Q));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_i8(d0, dp + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k > 0);
-          if (u < 8) trace_stamp(args, 16 + u);
-          umma_commit(&mma_done[u % C::A_PAIRS]);
-          if (u < 8) trace_stamp(args, 32 + u);
+          for (int k = 0; k < 4; ++k) umma_i8(d0 + ng4 * BN, dp + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc, k > 0);
         }
+        if (u < 8) trace_stamp(args, 16 + u);
+        if (ng4 > 0 && ((u & 1) == 1 || u == np4 - 1)) umma_commit(&q_empty[b & 1]);    // the batch's token tiles are consumed
+        umma_commit(&mma_done[ar]);          // accumulators ready AND operand slot reusable
+        if (u < 8) trace_stamp(args, 32 + u);
       }
       __syncwarp();
     }
@@ -362,7 +357,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     int staged_from = 0, staged_to = 0;      // groups [staged_from, staged_to) have their scale rows in shared memory
 
     for (int u = 0; u < nu; ++u) {
-      const int i0 = u < np4 ? 2 * u : n4, ng = u < np4 ? min(2, n4 - 2 * u) : 1;
+      const int i0 = 2 * u, ng = min(2, iters - 2 * u);
       if (i0 + ng > staged_to) {
         // ---- stage the scale rows of groups [i0, i0 + SC): weight scales first (no dependency), then activation scales
         const int cnt = min(C::SC, iters - i0);

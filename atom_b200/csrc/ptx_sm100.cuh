@@ -39,16 +39,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// A pipeline bug must not hang the GPU (and the box): after ~4 s the waiting thread reports the barrier and traps,
-// turning a deadlock into a launch error.  The clock is only consulted every 64 unsuccessful probes.
+// A pipeline bug must not hang the GPU (and the box): after ~4 s the waiting thread traps, turning a deadlock into a launch
+// error.  The clock is only consulted every 64 unsuccessful probes.  The trap is inline on purpose: a CALL (a noinline
+// reporter, printf) anywhere in a kernel makes ptxas keep every warp within the launch-bound register count, which defeats
+// setmaxnreg (measured: the 128 x 256 kernel's epilogue spilled 490 bytes until the call was gone).  -DATOM_MBAR_DEBUG
+// brings the diagnostic message back for debugging.
 #ifndef ATOM_MBAR_TIMEOUT_CYCLES
 #define ATOM_MBAR_TIMEOUT_CYCLES (8000000000ll)
 #endif
+#ifdef ATOM_MBAR_DEBUG
 __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
   printf("atom_b200: mbarrier wait timed out: block (%d,%d,%d) thread %d smem 0x%x parity %u\n", blockIdx.x, blockIdx.y,
          blockIdx.z, threadIdx.x, smem_u32(bar), parity);
   __trap();
 }
+#else
+__device__ __forceinline__ void mbar_timeout(uint64_t*, uint32_t) { asm volatile("trap;"); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = 0;

@@ -310,6 +310,8 @@ def main():
             with torch.cuda.graph(graph, stream=stream):
                 run_batch()
 
+    launch_desc = "one CUDA graph replay per step" if graph is not None else "python loop on the legacy stream (reference launcher)"
+
     def step():
         if graph is not None:
             graph.replay()
@@ -471,7 +473,7 @@ def main():
         "data": "synthetic", "impl": a.impl,
         "config": {"workload": f"gemm_i4_o16 M={M} N={N} K={K} (K incl. 128 INT8 keeper) group_size=128", "gemms_per_step": R_sets,
                    "l2": f"{R_sets} distinct operand sets per step = {R_sets * per_set / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                   "launch": "one CUDA graph replay per step" if graph is not None else "python loop on the legacy stream (reference launcher)",
+                   "launch": launch_desc,
                    "parallelism": f"dp{world} for the GEMM line (independent GEMM problems per rank, no collective); "
                                   f"tp{world} with two all-reduces per layer for the `tp` record",
                    "published_baseline": (f"{PUBLISHED_TOPS[M]} TOP/s on one RTX 4090 (BASELINE.md section 1, bench_gemm.png)"

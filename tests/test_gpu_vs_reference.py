@@ -61,7 +61,9 @@ def test_activate_equals_reference_kernel(m):
                                          (32, 5120, 5120, 1), (32, 13824, 5120, 1), (32, 5120, 13824, 1), (32, 1024, 8192, 1),
                                          (32, 8192, 2816, 1), (32, 8192, 2688, 1), (64, 8192, 1024, 1),
                                          # prefill: the 7B MLP up-projection and config #3's 16 x 2048 tokens
-                                         (4096, 11008, 4096, 0), (32768, 4096, 4096, 0)])
+                                         (4096, 11008, 4096, 0), (32768, 4096, 4096, 0),
+                                         # the same prefill shapes forced through each of the two prefill kernels
+                                         (4096, 4096, 4096, 512), (4096, 4096, 4096, 1024), (1000, 11008, 4096, 512)])
 def test_gemm_o16_equals_reference_kernel(m, n, k, flags):
     from atom_b200 import ops
     t = [T(x) for x in O.make_gemm_inputs(m, n, k, seed=m + n + k, pair_shared=(m % 2 == 0))]

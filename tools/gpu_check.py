@@ -149,6 +149,8 @@ def gtiming(ms_list, n=4096, k=4096):
         elif m <= 128:
             variants["skinny"] = 4
         if m > 64:
+            variants["tall128"] = 1024        # 128 x 128 tiles
+            variants["wide256"] = 512         # 128 x 256 tiles, token operand in tensor memory
             variants["legacy_tall"] = 256
         launches = nrot if m <= 512 else 6
         for name, flags in variants.items():
