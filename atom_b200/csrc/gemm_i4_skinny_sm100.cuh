@@ -265,33 +265,53 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     griddep_wait();                                       // the activations are the preceding kernel's output
     if (tq == 0) trace_stamp(args, 6);
     const int nbatch = (n4 + C::QB - 1) / C::QB;
-    for (int b = 0; b < nbatch; ++b) {
-      if (b >= 2) mbar_wait(&q_empty[b & 1], ((b >> 1) - 1) & 1);
+    // One pass = up to 256 chunks (4 per thread).  The loads of the NEXT pass are issued before the current one is expanded
+    // and stored, so the global-memory latency of consecutive batches overlaps (it is the longest item on the dependent path).
+    auto load_pass = [&](int b, int c0, uint4 (&w)[4]) {
       const int ng = min(C::QB, n4 - b * C::QB), chunks = ng * BN * 4;
-      for (int c0 = 0; c0 < chunks; c0 += 256) {
-        uint4 w[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const int c = c0 + x * 64 + tq;
-          w[x] = make_uint4(0, 0, 0, 0);
-          if (c < chunks) {
-            const int grp = c / (BN * 4), r = (c % (BN * 4)) >> 2, j = c & 3;
-            if (m0 + r < args.M)
-              w[x] = ld_cg_v4(args.a4 + (size_t)(m0 + r) * kp + (size_t)(g_begin + b * C::QB + grp) * 64 + j * 16);
-          }
+      for (int x = 0; x < 4; ++x) {
+        const int c = c0 + x * 64 + tq;
+        w[x] = make_uint4(0, 0, 0, 0);
+        if (c < chunks) {
+          const int grp = c / (BN * 4), r = (c % (BN * 4)) >> 2, j = c & 3;
+          if (m0 + r < args.M)
+            w[x] = ld_cg_v4(args.a4 + (size_t)(m0 + r) * kp + (size_t)(g_begin + b * C::QB + grp) * 64 + j * 16);
         }
+      }
+    };
+    auto store_pass = [&](int b, int c0, const uint4 (&w)[4]) {
+      const int ng = min(C::QB, n4 - b * C::QB), chunks = ng * BN * 4;
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const int c = c0 + x * 64 + tq;
-          if (c < chunks) {
-            const int grp = c / (BN * 4), r = (c % (BN * 4)) >> 2, j = c & 3;
-            uint4 lo, hi;
-            expand_chunk(w[x], lo, hi);
-            uint8_t* row = smem + C::OFF_EXP_Q + ((b * C::QB + grp) % C::QS) * C::EXP_Q + (r >> 3) * 1024 + (r & 7) * 128;
-            *reinterpret_cast<uint4*>(row + (((2 * j) ^ (r & 7)) << 4)) = lo;
-            *reinterpret_cast<uint4*>(row + (((2 * j + 1) ^ (r & 7)) << 4)) = hi;
-          }
+      for (int x = 0; x < 4; ++x) {
+        const int c = c0 + x * 64 + tq;
+        if (c < chunks) {
+          const int grp = c / (BN * 4), r = (c % (BN * 4)) >> 2, j = c & 3;
+          uint4 lo, hi;
+          expand_chunk(w[x], lo, hi);
+          uint8_t* row = smem + C::OFF_EXP_Q + ((b * C::QB + grp) % C::QS) * C::EXP_Q + (r >> 3) * 1024 + (r & 7) * 128;
+          *reinterpret_cast<uint4*>(row + (((2 * j) ^ (r & 7)) << 4)) = lo;
+          *reinterpret_cast<uint4*>(row + (((2 * j + 1) ^ (r & 7)) << 4)) = hi;
         }
+      }
+    };
+    constexpr int PASSES = BN * C::QB * 4 / 256;           // passes per full batch: 1 / 2 / 4
+    uint4 wa[4], wb[4];
+    if (nbatch > 0) load_pass(0, 0, wa);
+    for (int b = 0; b < nbatch; ++b) {
+      if (b >= 2) mbar_wait(&q_empty[b & 1], ((b >> 1) - 1) & 1);         // the slots this batch overwrites are free
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        // next pass: same batch, or the first pass of the next batch (its loads do not touch shared memory, so they may be
+        // issued before that batch's slots are known to be free)
+        const bool more = p + 1 < PASSES || b + 1 < nbatch;
+        const int nb = p + 1 < PASSES ? b : b + 1, nc0 = p + 1 < PASSES ? (p + 1) * 256 : 0;
+        if ((p & 1) == 0) { if (more) load_pass(nb, nc0, wb); store_pass(b, p * 256, wa); }
+        else              { if (more) load_pass(nb, nc0, wa); store_pass(b, p * 256, wb); }
+      }
+      if constexpr (PASSES & 1) {                           // odd number of passes per batch: the buffers swap roles per batch
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { const uint4 t4 = wa[x]; wa[x] = wb[x]; wb[x] = t4; }
       }
       fence_proxy_async_smem();            // generic-proxy stores -> visible to the MMA's operand fetch
       __syncwarp();

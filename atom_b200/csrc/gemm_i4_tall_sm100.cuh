@@ -290,35 +290,46 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
       mbar_wait(&mma_done[es], (s / C::RING) & 1);
       tc_fence_after();
       if (warp == 8 && lane == 0 && s < 16) trace_stamp(args, 104 + s);
-      for (int j = 0; j < ng; ++j) {
-        const bool keeper = (s * GS + j == args.G);
-        const uint8_t* slot = smem + C::OFF_SM + (ss * GS + j) * 512;
-        const __half2 pw = reinterpret_cast<const __half2*>(slot)[(row >> 4) * 8 + (row & 7)];
-        const __half2 sm2 = __half2half2(upper ? __high2half(pw) : __low2half(pw));
-        // pair scales of this row's half (even channel for rows 0-7 of each 16, odd for rows 8-15), 8 per LDS.128
-        const uint4* sel = reinterpret_cast<const uint4*>(slot + 256 + (upper ? 128 : 0) + colbase);
-        const uint32_t taddr = lane_addr + (uint32_t)((es * GS + j) * BN + colbase);
+      // The stage's 2 x 4 chunks of 16 columns are software-pipelined: the tcgen05.ld of chunk n+1 is in flight while chunk
+      // n is dequantised (an exposed TMEM round trip per chunk is what bounded this loop before: ~16 cycles per element).
+      uint32_t rbuf[2][16];
+      tmem_ld_32x32b_x16(lane_addr + (uint32_t)((es * GS) * BN + colbase), rbuf[0]);
 #pragma unroll
-        for (int c0 = 0; c0 < C::CPT; c0 += 16) {              // 16 columns = 8 channel pairs = one LDS.128
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(taddr + c0, r);
-          const uint4 sv = sel[c0 >> 4];
-          tmem_ld_wait();
-          tmem_st_32x32b_x16(taddr + c0, kAccBias);            // re-arm while the values are processed
-          if (c0 + 16 == C::CPT && j == ng - 1) {              // the stage's accumulators are read and re-armed
-            tmem_st_wait_();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[es]);
-          }
-          const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+      for (int j = 0; j < GS; ++j) {
+        if (j < ng) {
+          const bool keeper = (s * GS + j == args.G);
+          const uint8_t* slot = smem + C::OFF_SM + (ss * GS + j) * 512;
+          const __half2 pw = reinterpret_cast<const __half2*>(slot)[(row >> 4) * 8 + (row & 7)];
+          const __half2 sm2 = __half2half2(upper ? __high2half(pw) : __low2half(pw));
+          // pair scales of this row's half (even channel for rows 0-7 of each 16, odd for rows 8-15), 8 per LDS.128
+          const uint4* sel = reinterpret_cast<const uint4*>(slot + 256 + (upper ? 128 : 0) + colbase);
+          const uint32_t taddr = lane_addr + (uint32_t)((es * GS + j) * BN + colbase);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {                         // 4 columns: pairs (2q', 2q'+1) of this 16-column run
-            float2 rs = __half22float2(__hmul2(sm2, *reinterpret_cast<const __half2*>(&sw[q])));
-            if (keeper) { rs.x *= 256.f; rs.y *= 256.f; }       // keeper operands carry no 16 * 16 factor (exact)
-            const int k = c0 + 4 * q;
-            ffma2(acc[(k >> 1) + 0], unbias2(r[4 * q + 0], r[4 * q + 1]), rs);
-            ffma2(acc[(k >> 1) + 1], unbias2(r[4 * q + 2], r[4 * q + 3]), rs);
+          for (int c = 0; c < 4; ++c) {                          // 16 columns = 8 channel pairs = one LDS.128
+            const int n = j * 4 + c;                             // chunk number within the stage (compile-time after unrolling)
+            const uint4 sv = sel[c];
+            tmem_ld_wait();                                      // chunk n has landed in rbuf[n & 1]
+            const bool last = (c == 3 && j == ng - 1);
+            if (!last) {                                         // next chunk: same group, or the first of the stage's second group
+              const uint32_t nxt = (c < 3) ? taddr + 16 * (c + 1) : lane_addr + (uint32_t)((es * GS + j + 1) * BN + colbase);
+              tmem_ld_32x32b_x16(nxt, rbuf[(n + 1) & 1]);
+            }
+            tmem_st_32x32b_x16(taddr + 16 * c, kAccBias);        // re-arm the chunk just read
+            if (last) {                                          // the stage's accumulators are read and re-armed
+              tmem_st_wait_();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[es]);
+            }
+            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                         // 4 columns: pairs (2q', 2q'+1) of this 16-column run
+              float2 rs = __half22float2(__hmul2(sm2, *reinterpret_cast<const __half2*>(&sw[q])));
+              if (keeper) { rs.x *= 256.f; rs.y *= 256.f; }       // keeper operands carry no 16 * 16 factor (exact)
+              const int k = 16 * c + 4 * q;
+              ffma2(acc[(k >> 1) + 0], unbias2(rbuf[n & 1][4 * q + 0], rbuf[n & 1][4 * q + 1]), rs);
+              ffma2(acc[(k >> 1) + 1], unbias2(rbuf[n & 1][4 * q + 2], rbuf[n & 1][4 * q + 3]), rs);
+            }
           }
         }
       }

@@ -109,7 +109,7 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
   if (threadIdx.x == 0) trace_stamp(args, 1);
 
   if (warp < 4) {
-    reg_dealloc<64>();
+    reg_dealloc<56>();
     if (warp == 0) {
       // ============================================================ TMA producer (INT4 groups; the keeper is loaded by a converter)
       griddep_wait();                                // token tiles are the preceding kernel's output
@@ -179,7 +179,7 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
     }
   } else if (warp < 8) {
     // ============================================================ converters
-    reg_dealloc<112>();
+    reg_dealloc<104>();
     const int wq = warp & 3, row = wq * 32 + lane, t = (warp - 4) * 32 + lane;
     const int xr = (row >> 1) & 3;                       // SWIZZLE_64B: 16-B chunk index ^= address bits [7,9)
     for (int g = 0; g < groups; ++g) {
@@ -231,7 +231,7 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
     }
   } else {
     // ============================================================ epilogue warpgroups: thread = token row, 64 columns of each half
-    reg_alloc<168>();
+    reg_alloc<176>();
     const int wq = warp & 3, row = wq * 32 + lane;
     const int colbase = ((warp - 8) >> 2) * 64;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + C::D_COL0;
@@ -259,22 +259,32 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
       const uint8_t* slot = smem + C::OFF_SM + ss * C::SCALE_BYTES;
       const __half2 pw = reinterpret_cast<const __half2*>(slot)[(row >> 4) * 8 + (row & 7)];
       const __half2 sm2 = __half2half2(upper ? __high2half(pw) : __low2half(pw));
+      // 2 halves x 4 chunks of 16 columns, software-pipelined: the tcgen05.ld of the next chunk is in flight while the
+      // current one is dequantised (an exposed TMEM round trip per chunk costs ~16 cycles per element otherwise)
+      uint32_t rbuf[2][16];
+      mbar_wait(&mma_done[0], g & 1);
+      tc_fence_after();
+      if (warp == 8 && lane == 0 && g < 8) trace_stamp(args, 104 + g);
+      tmem_ld_32x32b_x16(lane_addr + (uint32_t)colbase, rbuf[0]);
 #pragma unroll
       for (int h = 0; h < C::NH; ++h) {
         if (h < nh) {
-          mbar_wait(&mma_done[h], g & 1);
-          tc_fence_after();
-          if (warp == 8 && lane == 0 && h == 0 && g < 8) trace_stamp(args, 104 + g);
           const uint4* sel = reinterpret_cast<const uint4*>(slot + 256 + 256 * h + (upper ? 128 : 0) + colbase);
           const uint32_t taddr = lane_addr + (uint32_t)(h * C::BH + colbase);
 #pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 16) {              // 16 columns = 8 channel pairs = one LDS.128
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(taddr + c0, r);
-            const uint4 sv = sel[c0 >> 4];
-            tmem_ld_wait();
-            tmem_st_32x32b_x16(taddr + c0, kAccBias);        // re-arm while the values are processed
-            if (c0 + 16 == 64) {
+          for (int c = 0; c < 4; ++c) {                          // 16 columns = 8 channel pairs = one LDS.128
+            const int n = h * 4 + c;
+            const uint4 sv = sel[c];
+            tmem_ld_wait();                                      // chunk n has landed in rbuf[n & 1]
+            if (c < 3) {
+              tmem_ld_32x32b_x16(taddr + 16 * (c + 1), rbuf[(n + 1) & 1]);
+            } else if (h + 1 < nh) {                             // first chunk of the other half: its MMAs must be complete
+              mbar_wait(&mma_done[h + 1], g & 1);
+              tc_fence_after();
+              tmem_ld_32x32b_x16(lane_addr + (uint32_t)((h + 1) * C::BH + colbase), rbuf[(n + 1) & 1]);
+            }
+            tmem_st_32x32b_x16(taddr + 16 * c, kAccBias);        // re-arm the chunk just read
+            if (c == 3) {                                        // this half's accumulator is read and re-armed
               tmem_st_wait_();
               tc_fence_before();
               __syncwarp();
@@ -284,10 +294,10 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float2 rs = __half22float2(__hmul2(sm2, *reinterpret_cast<const __half2*>(&sw[q])));
-              if (keeper) { rs.x *= 256.f; rs.y *= 256.f; }   // keeper operands carry no 16 * 16 factor (exact)
-              const int k = c0 + 4 * q;
-              ffma2(acc[h][(k >> 1) + 0], unbias2(r[4 * q + 0], r[4 * q + 1]), rs);
-              ffma2(acc[h][(k >> 1) + 1], unbias2(r[4 * q + 2], r[4 * q + 3]), rs);
+              if (keeper) { rs.x *= 256.f; rs.y *= 256.f; }       // keeper operands carry no 16 * 16 factor (exact)
+              const int k = 16 * c + 4 * q;
+              ffma2(acc[h][(k >> 1) + 0], unbias2(rbuf[n & 1][4 * q + 0], rbuf[n & 1][4 * q + 1]), rs);
+              ffma2(acc[h][(k >> 1) + 1], unbias2(rbuf[n & 1][4 * q + 2], rbuf[n & 1][4 * q + 3]), rs);
             }
           }
         }

@@ -1,14 +1,12 @@
-"""GPU suite, OPT-IN (ATOM_EXPERIMENTAL=1): programmatic dependent launch (atom_set_pdl / ATOM_B200_PDL=1).  Written after the
-round-1 GPU budget was spent, never executed on hardware.  PDL must not change a single bit: every chain is run with plain
-stream order first and with PDL second (eagerly and from a CUDA graph) and compared for equality."""
-import os
-
+"""GPU suite: programmatic dependent launch.  The GEMM kernels are always launched with programmatic stream serialization
+(they fetch only weights before griddepcontrol.wait); atom_set_pdl(1) / ATOM_B200_PDL=1 extends it to the quantise and KV
+kernels (they then signal launch_dependents at once, so the GEMM behind them streams its weights while they run).  PDL must
+not change a single bit: every chain is run with it off first and on second (eagerly and from a CUDA graph)."""
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("ATOM_EXPERIMENTAL") != "1",
-                                                  reason="experimental launch mode: set ATOM_EXPERIMENTAL=1 to run")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture

@@ -194,6 +194,45 @@ def trace(m, flags, n=4096, k=4096):
     print(json.dumps(out), flush=True)
 
 
+def trace_warm(m, flags, n=4096, k=4096):
+    """Pipeline stamps of the LAST launch of a replayed graph of back-to-back GEMMs on rotating operand sets (steady state,
+    programmatic dependent launch active): per-CTA intervals relative to the CTA's own start, median / p10 / p90 over CTAs."""
+    from atom_b200 import _lib
+    base = O.make_gemm_inputs(m, n, k, seed=1)
+    per_set = sum(x.nbytes for x in base)
+    nrot = max(3, int(300e6 // per_set) + 1)
+    sets = [[T(x) for x in base] for _ in range(nrot)]
+    buf = torch.zeros((4096, 128), dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for i in range(3):
+            ops.dense_layer_gemm_i4_fp16(*sets[i], flags=flags)
+        st.synchronize()
+        _lib.lib().atom_gemm_set_trace(buf.data_ptr())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for i in range(nrot):
+                ops.dense_layer_gemm_i4_fp16(*sets[i], flags=flags)
+        _lib.lib().atom_gemm_set_trace(None)
+        for _ in range(3):
+            g.replay()
+        st.synchronize()
+    b = buf.cpu().numpy()
+    used = np.nonzero(b[:, 0])[0]
+    rel = (b[used] - b[used, 0:1]).astype(np.float64)
+    rel[b[used] == 0] = np.nan
+    def q(col):
+        v = rel[:, col]; v = v[~np.isnan(v)]
+        return None if len(v) == 0 else [int(np.percentile(v, p)) for p in (10, 50, 90)]
+    out = {"trace_warm": [m, n, k, flags], "ctas": int(len(used)), "p10_p50_p90_cycles_from_cta_start": {
+        "setup_done": q(1), "dependency_resolved": q(6), "q_batch0_ready": q(5), "scales_staged": q(7),
+        "first_weights_landed": q(40), "first_unit_converted": q(72), "mma_woke_0": q(88), "mma_woke_1": q(89), "mma_woke_2": q(90), "mma_woke_3": q(91),
+        "acc_ready_0": q(104), "acc_ready_3": q(107), "epi_done_0": q(120), "epi_done_3": q(123),
+        "epi_loop_done": q(2), "reduced": q(3), "end": q(4)}}
+    # spread of CTA start times of the last launch (global clock64 differs per SM only by a constant offset: informative only)
+    print(json.dumps(out), flush=True)
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "diag":
@@ -217,5 +256,7 @@ if __name__ == "__main__":
             del sets
     elif cmd == "trace":
         trace(int(sys.argv[2]), int(sys.argv[3]))
+    elif cmd == "tracew":
+        trace_warm(int(sys.argv[2]), int(sys.argv[3]))
     elif cmd == "time":
         timing([int(x) for x in sys.argv[2:]] or [16, 32, 64, 128, 256, 512, 1024, 2048, 4096])

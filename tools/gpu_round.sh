@@ -29,7 +29,8 @@ for s in $STEPS; do case $s in
            timeout 300 python tools/gpu_check.py gshape 2>> $OUT/sk_gtime.err | tee $OUT/sk_gshape.jsonl
            timeout 300 python tools/gpu_check.py gtime 128 256 1024 4096 2>> $OUT/sk_gtime.err | tee $OUT/tall_gtime.jsonl
            : > $OUT/sk_trace.jsonl
-           for cfg in "16 0" "16 1" "4096 512" "4096 1024"; do timeout 120 python tools/gpu_check.py trace $cfg 2>&1 | tail -1 | tee -a $OUT/sk_trace.jsonl | cut -c1-2500; done ;;
+           for cfg in "16 0" "16 1" "4096 512" "4096 1024"; do timeout 120 python tools/gpu_check.py trace $cfg 2>&1 | tail -1 | tee -a $OUT/sk_trace.jsonl | cut -c1-2500; done
+           for cfg in "16 0" "16 1"; do timeout 120 python tools/gpu_check.py tracew $cfg 2>&1 | tail -1 | tee -a $OUT/sk_trace.jsonl | cut -c1-2500; done ;;
   dec)     echo "== decode attention: parity at 5e-4, timing, ncu capture"
            timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py -m gpu -q --timeout=300 -p no:cacheprovider -k "decode or rmsnorm" > $OUT/pytest_dec.txt 2>&1; echo "rc=$?"; tail -15 $OUT/pytest_dec.txt
            timeout 300 python tools/layer_bench.py 2>&1 | tail -1 | tee $OUT/layer_7b.json
