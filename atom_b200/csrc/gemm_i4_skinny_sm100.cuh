@@ -228,6 +228,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     for (int u = 0; u < nu; ++u) {
       const int as = u % C::ACC_PAIRS, ar = u % C::A_PAIRS, b = u >> 1;           // QB = 4 groups = 2 units per token batch
       const int ng = min(2, iters - 2 * u), ng4 = max(0, min(2, n4 - 2 * u));    // groups of the unit, of which INT4
+      if (lane == 0 && u < 8) trace_stamp(args, 96 + u);
       if (u >= C::ACC_PAIRS) mbar_wait(&acc_empty[as], ((u / C::ACC_PAIRS) - 1) & 1);
       const uint32_t d0 = tmem_base + C::ACC_COL0 + as * 2 * BN;
       if (ng4 > 0) {

@@ -41,7 +41,9 @@ struct TallCfg {
   static constexpr int TMEM_COLS = RING * GS * BN;                // 512
   static constexpr int SCALE_STAGES = 4;
   static constexpr int EPI_WGS = 2, CPT = BN / EPI_WGS;           // 64 accumulator columns per epilogue thread
-  static constexpr int THREADS = 512;
+  static constexpr int CONV_WARPS = 8;                            // the converters are latency-bound: 653 cycles per group with 4 warps (tools/microbench)
+  static constexpr int EPI_WARP0 = 4 + CONV_WARPS;                // first epilogue warp
+  static constexpr int THREADS = 32 * (EPI_WARP0 + 4 * EPI_WGS);  // 640
   static constexpr int PACK_T = 128 * 64, EXP_T = 128 * 128;      // bytes per packed / expanded group tile
   static constexpr int OFF_EXP_P = 0;
   static constexpr int OFF_EXP_Q = OFF_EXP_P + RING * GS * EXP_T;
@@ -56,6 +58,9 @@ struct TallCfg {
 };
 
 constexpr uint32_t kAccBias = 0x4B400000u;   // bit pattern of 12582912.0f
+
+template <int kRegs> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, uint32_t v) {
   asm volatile(
@@ -136,8 +141,8 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
     fence_barrier_init();
     for (int s = 0; s < s_w; ++s) issue_stage(s, s, 1);   // weights first
     tma_prefetch_desc(&tm_p8); tma_prefetch_desc(&tm_q8);
-    for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_empty[i], 4);
-    for (int i = 0; i < C::RING; ++i) { mbar_init(&exp_full[i], 4); mbar_init(&mma_done[i], 1); mbar_init(&tmem_empty[i], 4 * C::EPI_WGS); }
+    for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_empty[i], C::CONV_WARPS);
+    for (int i = 0; i < C::RING; ++i) { mbar_init(&exp_full[i], C::CONV_WARPS); mbar_init(&mma_done[i], 1); mbar_init(&tmem_empty[i], 4 * C::EPI_WGS); }
     for (int i = 0; i < C::SCALE_STAGES; ++i) { mbar_init(&scale_full[i], 32); mbar_init(&scale_empty[i], 4 * C::EPI_WGS); }
     fence_barrier_init();
   }
@@ -148,7 +153,10 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) trace_stamp(args, 1);
 
+  // 640 threads => 96 registers each at launch; the service warpgroup hands its surplus to the two epilogue warpgroups
+  // (40 + 2 x 96 + 2 x 136 <= 512 register slices of 128 threads)
   if (warp < 4) {
+    reg_dealloc<40>();
     if (warp == 0) {
       // ============================================================ TMA producer (warp loops, one elected lane issues)
       griddep_wait();                              // the token tiles are the preceding kernel's output
@@ -226,7 +234,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
         mbar_arrive(&scale_full[ss]);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < C::EPI_WARP0) {
     // ============================================================ converter warps
     const int t = (warp - 4) * 32 + lane;
     for (int s = 0; s < nstages; ++s) {
@@ -240,8 +248,8 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
 #pragma unroll
         for (int j = 0; j < GS; ++j) {
           if (j < n4) {
-            convert_tile<128, 128>(smem + C::OFF_PACK_P + (ps * GS + j) * C::PACK_T, smem + C::OFF_EXP_P + (es * GS + j) * C::EXP_T, t);
-            convert_tile<128, 128>(smem + C::OFF_PACK_Q + (ps * GS + j) * C::PACK_T, smem + C::OFF_EXP_Q + (es * GS + j) * C::EXP_T, t);
+            convert_tile<128, 32 * C::CONV_WARPS>(smem + C::OFF_PACK_P + (ps * GS + j) * C::PACK_T, smem + C::OFF_EXP_P + (es * GS + j) * C::EXP_T, t);
+            convert_tile<128, 32 * C::CONV_WARPS>(smem + C::OFF_PACK_Q + (ps * GS + j) * C::PACK_T, smem + C::OFF_EXP_Q + (es * GS + j) * C::EXP_T, t);
           }
         }
         if (t == 0 && s < 16) trace_stamp(args, 56 + s);
@@ -263,9 +271,10 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
     }
   } else {
     // ============================================================ epilogue warpgroups
+    reg_alloc<136>();
     const int wq = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = wq * 32 + lane;                // token row == TMEM lane
-    const int colbase = ((warp - 8) >> 2) * C::CPT;
+    const int colbase = ((warp - C::EPI_WARP0) >> 2) * C::CPT;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
     // arm every accumulator slot with the bias pattern (completion #0 of tmem_empty)
 #pragma unroll
@@ -289,7 +298,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
       mbar_wait(&scale_full[ss], (s / C::SCALE_STAGES) & 1);
       mbar_wait(&mma_done[es], (s / C::RING) & 1);
       tc_fence_after();
-      if (warp == 8 && lane == 0 && s < 16) trace_stamp(args, 104 + s);
+      if (warp == C::EPI_WARP0 && lane == 0 && s < 16) trace_stamp(args, 104 + s);
       // The stage's 2 x 4 chunks of 16 columns are software-pipelined: the tcgen05.ld of chunk n+1 is in flight while chunk
       // n is dequantised (an exposed TMEM round trip per chunk is what bounded this loop before: ~16 cycles per element).
       uint32_t rbuf[2][16];
@@ -335,9 +344,9 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&scale_empty[ss]);       // this warp no longer reads the stage's scales
-      if (warp == 8 && lane == 0 && s < 8) trace_stamp(args, 120 + s);
+      if (warp == C::EPI_WARP0 && lane == 0 && s < 8) trace_stamp(args, 120 + s);
     }
-    if (warp == 8 && lane == 0) trace_stamp(args, 2);
+    if (warp == C::EPI_WARP0 && lane == 0) trace_stamp(args, 2);
     griddep_wait();                                        // the output buffer may still be read by the preceding kernel
 
     // ------------------------------------------------------------ output.  acc[i] = positions (2i, 2i+1); channel of
@@ -373,7 +382,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
         const float a0 = fabsf(acc[i].x), a1 = fabsf(acc[i].y);
         mx = fmaxf(mx, fmaxf(a0, a1)); mn = fminf(mn, fminf(a0, a1));
       }
-      const int part = (warp - 8) >> 2;
+      const int part = (warp - C::EPI_WARP0) >> 2;
       xch[(part * 2 + 0) * C::BM + row] = mx;
       xch[(part * 2 + 1) * C::BM + row] = mn;
       asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -81,7 +81,13 @@ ATOM_API int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, in
 /* replaces dense_layer_gemm_i4_fp16 (punica_ops.cc:226-237 -> DenseLayerGEMM_i4<nv_half>, DenseLayerGEMM_i4.cu:723-793)
  *   a u8 [M,(K-128)/2]  b u8 [N,(K-128)/2]  a_scale f16 [K/128-1, scale_size(M)]  b_scale f16 [K/128-1, N]
  *   a_keeper i8 [M,128] b_keeper i8 [N,128] a_keeper_scale f16 [scale_size(M)]    b_keeper_scale f16 [N]
- *   d f16 [M,N].   K includes the 128 keeper channels (as in the e2e launcher).  N % 8 == 0, K % 128 == 0, K >= 256. */
+ *   d f16 [M,N].   K includes the 128 keeper channels (as in the e2e launcher).  N % 8 == 0, K % 128 == 0, K >= 256.
+ * Bit-identity: every path accumulates the groups in the reference's order (0..G-1, keeper last) and is bit-identical to the
+ * reference kernel, EXCEPT flags = ATOM_GEMM_AUTO with M <= 64 when the dispatcher splits K over a cluster (channel tiles
+ * alone would not fill the GPU): the FP32 partials are then summed per K slice, <= 1 fp16 ulp on < 2 % of the outputs (inside
+ * the operator's 1e-3 contract).  ATOM_GEMM_NO_SPLITK restores the reference's order at decode sizes.
+ * The weights (b, b_scale, b_keeper, b_keeper_scale) are read before the preceding kernel on `stream` has completed
+ * (programmatic dependent launch): they must not be written by the kernel launched immediately before this call. */
 ATOM_API int atom_gemm_i4_o16(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
                      const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d, int64_t M,
                      int64_t N, int64_t K, uint32_t flags, void* stream);

@@ -187,7 +187,8 @@ def trace(m, flags, n=4096, k=4096):
              "q_batch0_ready": rel(r[5]), "dependency_resolved": rel(r[6]), "scales_staged": rel(r[7])}
         for i, nm in enumerate(names):
             d[nm] = [rel(x) for x in r[8 + 16 * i:8 + 16 * i + 8]]
-        d["mma_issued"] = [rel(x) for x in r[16:24]]          # decode kernel only (slots free there)
+        d["mma_loop_top"] = [rel(x) for x in r[96:104]]       # decode kernel only (slots free there)
+        d["mma_issued"] = [rel(x) for x in r[16:24]]
         d["mma_committed"] = [rel(x) for x in r[32:40]]
         d["epi_done"] = [rel(x) for x in r[120:128]]
         out[f"cta{cta}"] = d
@@ -226,7 +227,8 @@ def trace_warm(m, flags, n=4096, k=4096):
         return None if len(v) == 0 else [int(np.percentile(v, p)) for p in (10, 50, 90)]
     out = {"trace_warm": [m, n, k, flags], "ctas": int(len(used)), "p10_p50_p90_cycles_from_cta_start": {
         "setup_done": q(1), "dependency_resolved": q(6), "q_batch0_ready": q(5), "scales_staged": q(7),
-        "first_weights_landed": q(40), "first_unit_converted": q(72), "mma_woke_0": q(88), "mma_woke_1": q(89), "mma_woke_2": q(90), "mma_woke_3": q(91),
+        "first_weights_landed": q(40), "first_unit_converted": q(72), "mma_top_0": q(96), "mma_woke_0": q(88), "mma_issued_0": q(16), "mma_committed_0": q(32), "mma_top_1": q(97), "mma_woke_1": q(89),
+        "mma_top_2": q(98), "mma_woke_2": q(90), "mma_top_3": q(99), "mma_woke_3": q(91),
         "acc_ready_0": q(104), "acc_ready_3": q(107), "epi_done_0": q(120), "epi_done_3": q(123),
         "epi_loop_done": q(2), "reduced": q(3), "end": q(4)}}
     # spread of CTA start times of the last launch (global clock64 differs per SM only by a constant offset: informative only)

@@ -35,5 +35,11 @@ for s in $STEPS; do case $s in
            timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py -m gpu -q --timeout=300 -p no:cacheprovider -k "decode or rmsnorm" > $OUT/pytest_dec.txt 2>&1; echo "rc=$?"; tail -15 $OUT/pytest_dec.txt
            timeout 300 python tools/layer_bench.py 2>&1 | tail -1 | tee $OUT/layer_7b.json
            timeout 300 ncu --set full --clock-control none --import-source on -k regex:batch_decode -s 2 -c 1 -f -o $OUT/prof_decode python tools/layer_bench.py --copies 1 > /dev/null 2>&1; ls -la $OUT/prof_decode.ncu-rep ;;
+  ncug)    echo "== ncu: prefill GEMM kernels at M=4096 (128x128 and 128x256 tiles), decode GEMM at M=16"
+           FULL="--set full --clock-control none --import-source on"
+           timeout 300 ncu $FULL -k regex:gemm_i4_tall -s 3 -c 1 -f -o $OUT/prof_gemm_m4096_tall128 python tools/prof_gemm.py 4096 1024 > /dev/null 2>&1
+           timeout 300 ncu $FULL -k regex:gemm_i4_wide -s 3 -c 1 -f -o $OUT/prof_gemm_m4096_wide256 python tools/prof_gemm.py 4096 512 > /dev/null 2>&1
+           timeout 300 ncu $FULL -k regex:gemm_i4_skinny -s 3 -c 1 -f -o $OUT/prof_gemm_m16_skinny python tools/prof_gemm.py 16 0 > /dev/null 2>&1
+           ls -la $OUT/prof_gemm_*.ncu-rep ;;
   *) echo "unknown step $s" ;;
 esac; done
