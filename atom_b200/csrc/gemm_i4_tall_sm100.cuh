@@ -153,8 +153,9 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) trace_stamp(args, 1);
 
-  // 640 threads => 96 registers each at launch; the service warpgroup hands its surplus to the two epilogue warpgroups
-  // (40 + 2 x 96 + 2 x 136 <= 512 register slices of 128 threads)
+  // 640 threads => 96 registers each at launch.  setmaxnreg.inc can only claim what warps of the SAME CTA released (CTA pool):
+  // service 96 -> 40 and the two converter warpgroups 96 -> 80 release 56 + 2 x 16 = 88 slices of 128 registers, the two
+  // epilogue warpgroups claim 2 x (136 - 96) = 80
   if (warp < 4) {
     reg_dealloc<40>();
     if (warp == 0) {
@@ -236,6 +237,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
     }
   } else if (warp < C::EPI_WARP0) {
     // ============================================================ converter warps
+    reg_dealloc<80>();
     const int t = (warp - 4) * 32 + lane;
     for (int s = 0; s < nstages; ++s) {
       const int es = s % C::RING, ps = s % C::PACK;
