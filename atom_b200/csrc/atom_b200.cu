@@ -381,10 +381,10 @@ int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t f
   // <swap, BN, groups per pipeline stage, packed stages, K split, o4, converter warps, epilogue warpgroups>
   if (!skinny) {
     if (flags & ATOM_GEMM_LEGACY_TALL) return launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream);
-    // 128 x 256 tiles (token operand in tensor memory) once they fill the machine, 128 x 128 tiles below
-    const int64_t wide_tiles = ((op.M + 127) / 128) * ((op.N + 255) / 256);
-    const bool wide = (flags & ATOM_GEMM_FORCE_WIDE) || (!(flags & ATOM_GEMM_NO_WIDE) && wide_tiles >= 120);
-    return wide ? launch_wide<kO4>(op, args, stream) : launch_tall<kO4>(op, args, stream);
+    // 128 x 128 tiles by default.  The 128 x 256 kernel (token operand in tensor memory) halves the token-side conversion
+    // per MMA but measured slower at every size (4096^3: 704 vs 783-829 TOP/s, its 128-accumulator epilogue spills), so it
+    // only runs on request.
+    return (flags & ATOM_GEMM_FORCE_WIDE) ? launch_wide<kO4>(op, args, stream) : launch_tall<kO4>(op, args, stream);
   }
   if (op.M <= 64 && !(flags & ATOM_GEMM_LEGACY_SKINNY)) return skinny_dispatch<kO4>(op, args, flags, stream);
   // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not

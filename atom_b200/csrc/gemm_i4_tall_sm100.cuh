@@ -41,9 +41,9 @@ struct TallCfg {
   static constexpr int TMEM_COLS = RING * GS * BN;                // 512
   static constexpr int SCALE_STAGES = 4;
   static constexpr int EPI_WGS = 2, CPT = BN / EPI_WGS;           // 64 accumulator columns per epilogue thread
-  static constexpr int CONV_WARPS = 8;                            // the converters are latency-bound: 653 cycles per group with 4 warps (tools/microbench)
+  static constexpr int CONV_WARPS = 4;                            // 8 measured slower (782 vs 829 TOP/s at 4096^3): the SM is issue-bound, not converter-latency-bound
   static constexpr int EPI_WARP0 = 4 + CONV_WARPS;                // first epilogue warp
-  static constexpr int THREADS = 32 * (EPI_WARP0 + 4 * EPI_WGS);  // 640
+  static constexpr int THREADS = 32 * (EPI_WARP0 + 4 * EPI_WGS);  // 512
   static constexpr int PACK_T = 128 * 64, EXP_T = 128 * 128;      // bytes per packed / expanded group tile
   static constexpr int OFF_EXP_P = 0;
   static constexpr int OFF_EXP_Q = OFF_EXP_P + RING * GS * EXP_T;
@@ -62,22 +62,40 @@ constexpr uint32_t kAccBias = 0x4B400000u;   // bit pattern of 12582912.0f
 template <int kRegs> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
-__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, uint32_t v) {
+// 16 registers that hold the bias pattern for the whole kernel: tcgen05.st needs 16 consecutive source registers, and a
+// plain constant (or anything ptxas can prove uniform) makes the compiler rebuild all 16 with MOVs before every store --
+// one MOV per accumulator element.  The vector is therefore read back from TMEM once (tcgen05.ld results are opaque).
+struct BiasRegs { uint32_t r[16]; };
+__device__ __forceinline__ BiasRegs make_bias_regs(uint32_t armed_taddr) {   // 16 columns at armed_taddr already hold kAccBias
+  BiasRegs b;
+  tmem_ld_32x32b_x16(armed_taddr, b.r);
+  tmem_ld_wait();
+  return b;
+}
+__device__ __forceinline__ void tmem_st_const_x16(uint32_t taddr, uint32_t v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
       ::"r"(taddr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const BiasRegs& b) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(b.r[0]), "r"(b.r[1]), "r"(b.r[2]), "r"(b.r[3]), "r"(b.r[4]), "r"(b.r[5]), "r"(b.r[6]), "r"(b.r[7]),
+        "r"(b.r[8]), "r"(b.r[9]), "r"(b.r[10]), "r"(b.r[11]), "r"(b.r[12]), "r"(b.r[13]), "r"(b.r[14]), "r"(b.r[15]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait_() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// {as_float(a), as_float(b)} - 12582912: the biased accumulator words as exact FP32 integers (one FADD2)
-__device__ __forceinline__ float2 unbias2(uint32_t a, uint32_t b) {
+// {as_float(a), as_float(b)} * mul - 12582912 * mul: the biased accumulator words as exact FP32 integers, times the group's
+// power-of-two factor (1 for INT4 groups, 256 for the keeper) -- one FFMA2, exact (24 significant bits, no rounding)
+__device__ __forceinline__ float2 unbias2(uint32_t a, uint32_t b, float mul, float nbias) {
   float2 r;
-  asm("{\n\t.reg .b64 t, u;\n\t"
+  asm("{\n\t.reg .b64 t, u, v;\n\t"
       "mov.b64 t, {%2, %3};\n\t"
-      "mov.b64 u, {0fCB400000, 0fCB400000};\n\t"
-      "add.rn.f32x2 t, t, u;\n\t"
+      "mov.b64 u, {%4, %4};\n\t"
+      "mov.b64 v, {%5, %5};\n\t"
+      "fma.rn.f32x2 t, t, u, v;\n\t"
       "mov.b64 {%0, %1}, t;\n\t}"
-      : "=f"(r.x), "=f"(r.y) : "r"(a), "r"(b));
+      : "=f"(r.x), "=f"(r.y) : "r"(a), "r"(b), "f"(mul), "f"(nbias));
   return r;
 }
 // acc = c * rs + acc per lane (FFMA2: two IEEE fmaf)
@@ -153,9 +171,9 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) trace_stamp(args, 1);
 
-  // 640 threads => 96 registers each at launch.  setmaxnreg.inc can only claim what warps of the SAME CTA released (CTA pool):
-  // service 96 -> 40 and the two converter warpgroups 96 -> 80 release 56 + 2 x 16 = 88 slices of 128 registers, the two
-  // epilogue warpgroups claim 2 x (136 - 96) = 80
+  // 512 threads => 128 registers each at launch.  setmaxnreg.inc can only claim what warps of the SAME CTA released (CTA
+  // pool; a claim beyond it spins forever): service 128 -> 40 and the converter warpgroup 128 -> 80 release 88 + 48 = 136
+  // slices of 128 registers, the two epilogue warpgroups claim 2 x (160 - 128) = 64
   if (warp < 4) {
     reg_dealloc<40>();
     if (warp == 0) {
@@ -273,7 +291,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
     }
   } else {
     // ============================================================ epilogue warpgroups
-    reg_alloc<136>();
+    reg_alloc<160>();
     const int wq = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = wq * 32 + lane;                // token row == TMEM lane
     const int colbase = ((warp - C::EPI_WARP0) >> 2) * C::CPT;
@@ -282,8 +300,9 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
 #pragma unroll
     for (int slot = 0; slot < C::RING * GS; ++slot)
 #pragma unroll
-      for (int c0 = 0; c0 < C::CPT; c0 += 16) tmem_st_32x32b_x16(lane_addr + slot * BN + colbase + c0, kAccBias);
+      for (int c0 = 0; c0 < C::CPT; c0 += 16) tmem_st_const_x16(lane_addr + slot * BN + colbase + c0, kAccBias);
     tmem_st_wait_();
+    const BiasRegs kBias = make_bias_regs(lane_addr + colbase);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) { for (int es = 0; es < C::RING; ++es) mbar_arrive(&tmem_empty[es]); }
@@ -308,7 +327,8 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
 #pragma unroll
       for (int j = 0; j < GS; ++j) {
         if (j < ng) {
-          const bool keeper = (s * GS + j == args.G);
+          // keeper operands carry no 16 * 16 factor: its exact sums are scaled by 2^8 while they are unbiased
+          const float mul = (s * GS + j == args.G) ? 256.f : 1.f, nbias = -12582912.f * mul;
           const uint8_t* slot = smem + C::OFF_SM + (ss * GS + j) * 512;
           const __half2 pw = reinterpret_cast<const __half2*>(slot)[(row >> 4) * 8 + (row & 7)];
           const __half2 sm2 = __half2half2(upper ? __high2half(pw) : __low2half(pw));
@@ -325,7 +345,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
               const uint32_t nxt = (c < 3) ? taddr + 16 * (c + 1) : lane_addr + (uint32_t)((es * GS + j + 1) * BN + colbase);
               tmem_ld_32x32b_x16(nxt, rbuf[(n + 1) & 1]);
             }
-            tmem_st_32x32b_x16(taddr + 16 * c, kAccBias);        // re-arm the chunk just read
+            tmem_st_32x32b_x16(taddr + 16 * c, kBias);           // re-arm the chunk just read
             if (last) {                                          // the stage's accumulators are read and re-armed
               tmem_st_wait_();
               tc_fence_before();
@@ -335,11 +355,10 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
             const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {                         // 4 columns: pairs (2q', 2q'+1) of this 16-column run
-              float2 rs = __half22float2(__hmul2(sm2, *reinterpret_cast<const __half2*>(&sw[q])));
-              if (keeper) { rs.x *= 256.f; rs.y *= 256.f; }       // keeper operands carry no 16 * 16 factor (exact)
+              const float2 rs = __half22float2(__hmul2(sm2, *reinterpret_cast<const __half2*>(&sw[q])));
               const int k = 16 * c + 4 * q;
-              ffma2(acc[(k >> 1) + 0], unbias2(rbuf[n & 1][4 * q + 0], rbuf[n & 1][4 * q + 1]), rs);
-              ffma2(acc[(k >> 1) + 1], unbias2(rbuf[n & 1][4 * q + 2], rbuf[n & 1][4 * q + 3]), rs);
+              ffma2(acc[(k >> 1) + 0], unbias2(rbuf[n & 1][4 * q + 0], rbuf[n & 1][4 * q + 1], mul, nbias), rs);
+              ffma2(acc[(k >> 1) + 1], unbias2(rbuf[n & 1][4 * q + 2], rbuf[n & 1][4 * q + 3], mul, nbias), rs);
             }
           }
         }

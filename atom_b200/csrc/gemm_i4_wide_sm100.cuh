@@ -154,7 +154,7 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
       griddep_wait();
       for (int g = 0; g < groups; ++g) {
         const int ss = g % C::SCALE_STAGES;
-        const bool keeper = (g == args.G);
+          const bool keeper = (g == args.G);
         const __half* as_row = keeper ? args.a_keeper_scale : args.a_scale + (size_t)g * args.lda_scale;
         const __half* bs_row = keeper ? args.b_keeper_scale : args.b_scale + (size_t)g * args.ldb_scale;
         uint32_t aw[2] = {0u, 0u};
@@ -236,7 +236,7 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
 #pragma unroll
     for (int h = 0; h < C::NH; ++h)
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) tmem_st_32x32b_x16(lane_addr + h * C::BH + colbase + c0, kAccBias);
+      for (int c0 = 0; c0 < 64; c0 += 16) tmem_st_const_x16(lane_addr + h * C::BH + colbase + c0, kAccBias);
     tmem_st_wait_();
     tc_fence_before();
     __syncwarp();
@@ -252,7 +252,7 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
 
     for (int g = 0; g < groups; ++g) {
       const int ss = g % C::SCALE_STAGES;
-      const bool keeper = (g == args.G);
+      const float mul = (g == args.G) ? 256.f : 1.f, nbias = -12582912.f * mul;   // keeper: exact sums x 2^8 (no 16 * 16 operand factor)
       mbar_wait(&scale_full[ss], (g / C::SCALE_STAGES) & 1);
       const uint8_t* slot = smem + C::OFF_SM + ss * C::SCALE_BYTES;
       const __half2 pw = reinterpret_cast<const __half2*>(slot)[(row >> 4) * 8 + (row & 7)];
@@ -281,7 +281,7 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
               tc_fence_after();
               tmem_ld_32x32b_x16(lane_addr + (uint32_t)((h + 1) * C::BH + colbase), rbuf[(n + 1) & 1]);
             }
-            tmem_st_32x32b_x16(taddr + 16 * c, kAccBias);        // re-arm the chunk just read
+            tmem_st_const_x16(taddr + 16 * c, kAccBias);      // re-arm the chunk just read
             if (c == 3) {                                        // this half's accumulator is read and re-armed
               tmem_st_wait_();
               tc_fence_before();
@@ -291,11 +291,10 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
             const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              float2 rs = __half22float2(__hmul2(sm2, *reinterpret_cast<const __half2*>(&sw[q])));
-              if (keeper) { rs.x *= 256.f; rs.y *= 256.f; }       // keeper operands carry no 16 * 16 factor (exact)
+              const float2 rs = __half22float2(__hmul2(sm2, *reinterpret_cast<const __half2*>(&sw[q])));
               const int k = 16 * c + 4 * q;
-              ffma2(acc[h][(k >> 1) + 0], unbias2(rbuf[n & 1][4 * q + 0], rbuf[n & 1][4 * q + 1]), rs);
-              ffma2(acc[h][(k >> 1) + 1], unbias2(rbuf[n & 1][4 * q + 2], rbuf[n & 1][4 * q + 3]), rs);
+              ffma2(acc[h][(k >> 1) + 0], unbias2(rbuf[n & 1][4 * q + 0], rbuf[n & 1][4 * q + 1], mul, nbias), rs);
+              ffma2(acc[h][(k >> 1) + 1], unbias2(rbuf[n & 1][4 * q + 2], rbuf[n & 1][4 * q + 3], mul, nbias), rs);
             }
           }
         }

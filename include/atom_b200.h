@@ -42,8 +42,8 @@ extern "C" {
 #define ATOM_GEMM_FORCE_SKINNY 4u /* channels on the MMA-M axis (requires M <= 128 per tile; any M works) */
 #define ATOM_GEMM_SPLITK2 16u     /* decode shapes: force a 2-way K split (default: chosen from the tile count) */
 #define ATOM_GEMM_SPLITK4 32u     /* decode shapes: force a 4-way K split */
-#define ATOM_GEMM_FORCE_WIDE 512u    /* prefill shapes: 128 x 256 tiles, token operand in tensor memory (default when they fill the GPU) */
-#define ATOM_GEMM_NO_WIDE 1024u      /* prefill shapes: always 128 x 128 tiles */
+#define ATOM_GEMM_FORCE_WIDE 512u    /* prefill shapes: 128 x 256 tiles, token operand in tensor memory (opt-in: measured slower than 128 x 128) */
+#define ATOM_GEMM_NO_WIDE 1024u      /* prefill shapes: always 128 x 128 tiles (the default; kept for callers that pass it) */
 #define ATOM_GEMM_LEGACY_TALL 256u   /* prefill shapes: the round-1 kernel (I2F + FFMA epilogue), kept for A/B timing */
 #define ATOM_GEMM_LEGACY_SKINNY 128u /* decode shapes: the round-1 kernel (weights expanded into shared memory), kept for A/B timing */
 
