@@ -81,9 +81,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// nibbles q and q+4 of `w` as exact halves: ((w >> 4q) & 0x000F000F) | 0x64006400 = (1024+n_q, 1024+n_{q+4}), minus 1024
-__device__ __forceinline__ __half2 nib2(uint32_t w, int q) {
-  const uint32_t u = ((w >> (4 * q)) & 0x000F000Fu) | 0x64006400u;
+// Nibbles q and q+4 of `w` as exact halves, one LOP3 + one HSUB2 per couple and one shift per word:
+//   q even: ((w >> 4q) & 0x000F000F) | 0x64006400 = (1024 + n_q, 1024 + n_{q+4})           -> minus 1024 = n
+//   q odd : ((w >> 4(q-1)) & 0x00F000F0) | 0x64006400 = (1024 + 16 n_q, 1024 + 16 n_{q+4})  -> minus 1024 = 16 n
+// (a nibble in mantissa bits 4..7 is worth 16 units of the 1024 binade).  The caller folds the 1/16 of the odd couples into
+// the factor it multiplies them with (scale / 16, exact).  w8 = w >> 8 serves q = 2, 3.
+__device__ __forceinline__ __half2 nib2x(uint32_t w, uint32_t w8, int q) {
+  const uint32_t src = (q & 2) ? w8 : w;
+  const uint32_t u = (src & ((q & 1) ? 0x00F000F0u : 0x000F000Fu)) | 0x64006400u;
   return __hsub2(*reinterpret_cast<const __half2*>(&u), __half2half2(__ushort_as_half(0x6400)));
 }
 
@@ -104,7 +109,8 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
   uint2* tabh = reinterpret_cast<uint2*>(smem_d + DEC_STAGES * stage_bytes);    // [8 couples][P][4 quarters] (cos2, sin2) half2
   float2* stepr = reinterpret_cast<float2*>(tabh + 8 * P * 4);     // [64]     e^{-j 4P theta_i}
   float2* brk = stepr + 64;                                         // [4 warps][64] FP32 query bracket per warp
-  float* merge = reinterpret_cast<float*>(brk + 4 * 64);            // [4 warps][4 quarters][34]
+  uint2* brkh = reinterpret_cast<uint2*>(brk + 4 * 64);             // [4 warps][4 quarters][8 couples] (re2, im2) half2 of the page in hand
+  float* merge = reinterpret_cast<float*>(brkh + 4 * 4 * 8);        // [4 warps][4 quarters][34]
   uint64_t* full = reinterpret_cast<uint64_t*>(merge + 4 * 4 * 34);
   uint64_t* empty = full + DEC_STAGES;
 
@@ -136,17 +142,23 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
     float sn, cs; sincosf((float)(DEC_CONSUMERS * P) * f, &sn, &cs);
     stepr[tid] = make_float2(cs, -sn);
   }
-  if (warp < DEC_CONSUMERS && ts == 0) {
-    // FP32 query bracket of this warp: zq e^{j (len-1 - warp*P) theta}; 4 lanes (c) x 16 pairs
+  if (warp < DEC_CONSUMERS) {
+    // FP32 query bracket of this warp: zq e^{j (len-1 - warp*P) theta}.  Lane (ts, c) owns couple u = ts of quarter c: the
+    // pairs ja = 8(u/4) + u%4 and ja + 4; it keeps the FP32 values in smem and publishes their half2 packing.
     const __half* qh = q + ((size_t)b * kv.H + h) * 128;
+    const int ja = 8 * (ts >> 2) + (ts & 3);
+    float2 v2[2];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int i = 16 * c + j;
+    for (int x = 0; x < 2; ++x) {
+      const int i = 16 * c + ja + 4 * x;
       const float f = exp2f(-(float)i * (kLog2Theta / 64.f));
       const float xr = __half2float(qh[i]), xi = __half2float(qh[i + 64]);
       float sn, cs; sincosf((float)(seq_len - 1 - warp * P) * f, &sn, &cs);
-      brk[warp * 64 + i] = make_float2(xr * cs - xi * sn, xi * cs + xr * sn);
+      v2[x] = make_float2(xr * cs - xi * sn, xi * cs + xr * sn);
+      brk[warp * 64 + i] = v2[x];
     }
+    const __half2 re2 = __floats2half2_rn(v2[0].x, v2[1].x), im2 = __floats2half2_rn(v2[0].y, v2[1].y);
+    brkh[(warp * 4 + c) * 8 + ts] = make_uint2(*reinterpret_cast<const uint32_t*>(&re2), *reinterpret_cast<const uint32_t*>(&im2));
   }
   __syncthreads();
 
@@ -175,28 +187,34 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   const int tpl = P >> 3;                                          // tokens per lane per page
   float2* mybrk = brk + warp * 64 + 16 * c;
+  uint2* mybrkh = brkh + (warp * 4 + c) * 8;
 
   for (int pg = warp; pg < npages; pg += DEC_CONSUMERS) {
     const int s = pg % DEC_STAGES;
     const int valid = (pg == npages - 1) ? last_valid : P;
-    // this page's query bracket as half2 couples (j, j+4); then advance the FP32 copy to the warp's next page
+    // this page's query bracket as half2 couples (j, j+4); then every lane advances its own couple to the warp's next
+    // page (FP32 in smem, constant rotation e^{-j 4P theta}) and publishes the new half2 packing
     __half2 qre2[8], qim2[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int ja = 8 * (u >> 2) + (u & 3);
-      const float2 a = mybrk[ja], bb = mybrk[ja + 4];
-      qre2[u] = __floats2half2_rn(a.x, bb.x);
-      qim2[u] = __floats2half2_rn(a.y, bb.y);
+      const uint2 t = mybrkh[u];
+      qre2[u] = *reinterpret_cast<const __half2*>(&t.x);
+      qim2[u] = *reinterpret_cast<const __half2*>(&t.y);
     }
     __syncwarp();
-    if (ts == 0) {
+    {
+      const int ja = 8 * (ts >> 2) + (ts & 3);
+      float2 v2[2];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float2 st2 = stepr[16 * c + j], v = mybrk[j];
-        mybrk[j] = make_float2(v.x * st2.x - v.y * st2.y, v.y * st2.x + v.x * st2.y);
+      for (int x = 0; x < 2; ++x) {
+        const float2 st2 = stepr[16 * c + ja + 4 * x], v = mybrk[ja + 4 * x];
+        v2[x] = make_float2(v.x * st2.x - v.y * st2.y, v.y * st2.x + v.x * st2.y);
+        mybrk[ja + 4 * x] = v2[x];
       }
+      const __half2 re2 = __floats2half2_rn(v2[0].x, v2[1].x), im2 = __floats2half2_rn(v2[0].y, v2[1].y);
+      mybrkh[ts] = make_uint2(*reinterpret_cast<const uint32_t*>(&re2), *reinterpret_cast<const uint32_t*>(&im2));
     }
-    __syncwarp();
+    // (the __syncwarp() at the end of the page orders these writes before the next page's reads)
     mbar_wait(&full[s], (pg / DEC_STAGES) & 1);
     const uint8_t* st = ring + s * stage_bytes;
     const uint8_t* kblk = st;
@@ -222,12 +240,15 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
         const uint2 k_hi = swp ? k_a : k_b;                                    // elements 64+16c ..       (im)
         const __half2 kp = kpar[tl];
         const __half2 ks2 = __half2half2(__low2half(kp)), kz2 = __hneg2(__half2half2(__high2half(kp)));
+        const __half2 ks2o = __hmul2(ks2, __half2half2(__ushort_as_half(0x2C00)));   // scale / 16 for the odd couples (nib2x)
+        const uint32_t kl8[2] = {k_lo.x >> 8, k_lo.y >> 8}, kh8[2] = {k_hi.x >> 8, k_hi.y >> 8};
         const uint2* trow = tabh + tl * 4 + c;
         float xa = 0.f, xb = 0.f;        // q.k is accumulated in FP32 (the reference's compute_qk is all-FP32, decode.cuh:92-124)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const uint32_t wl = (u < 4) ? k_lo.x : k_lo.y, wh = (u < 4) ? k_hi.x : k_hi.y;
-          const __half2 kre = __hfma2(nib2(wl, u & 3), ks2, kz2), kim = __hfma2(nib2(wh, u & 3), ks2, kz2);
+          const __half2 sc2 = (u & 1) ? ks2o : ks2;
+          const __half2 kre = __hfma2(nib2x(wl, kl8[u >> 2], u & 3), sc2, kz2), kim = __hfma2(nib2x(wh, kh8[u >> 2], u & 3), sc2, kz2);
           const uint2 t = trow[u * P * 4];
           const __half2 c2 = *reinterpret_cast<const __half2*>(&t.x), s2 = *reinterpret_cast<const __half2*>(&t.y);
           const __half2 rr = __hfma2(kre, c2, __hneg2(__hmul2(kim, s2)));      // Re(zk e^{j t_lo theta})
@@ -246,9 +267,11 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
     const float m_new = fmaxf(m, xmax);
     const float sc = exp2f(m - m_new);
     m = m_new;
-    d *= sc; zsum *= sc;
+    if (__any_sync(0xffffffffu, sc != 1.f)) {     // once the running maxima have settled no lane of the warp rescales
+      d *= sc; zsum *= sc;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] *= sc;
+      for (int i = 0; i < 32; ++i) acc[i] *= sc;
+    }
     __half2 pv[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) pv[u] = __half2half2(__ushort_as_half(0));
@@ -262,10 +285,11 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
           const float p = exp2f(x[i] - m_new);
           d += p;
           zsum = fmaf(p, vp.y, zsum);
-          const __half2 ps2 = __float2half2_rn(p * vp.x);
+          const __half2 ps2 = __float2half2_rn(p * vp.x), ps2o = __float2half2_rn(p * vp.x * 0.0625f);
           const uint32_t w4[4] = {vw.x, vw.y, vw.z, vw.w};
+          const uint32_t w8[4] = {vw.x >> 8, vw.y >> 8, vw.z >> 8, vw.w >> 8};
 #pragma unroll
-          for (int u = 0; u < 16; ++u) pv[u] = __hfma2(nib2(w4[u >> 2], u & 3), ps2, pv[u]);
+          for (int u = 0; u < 16; ++u) pv[u] = __hfma2(nib2x(w4[u >> 2], w8[u >> 2], u & 3), (u & 1) ? ps2o : ps2, pv[u]);
         }
       }
     }
