@@ -641,8 +641,7 @@ int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, const void
   ATOM_REQUIRE(aligned16(kv_data) && aligned16(kv_param), "batch_decode_i4: KV pool must be 16-byte aligned");
   atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
                   (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
-  const size_t smem = (size_t)atom::DEC_STAGES * (136 * page_size) + (size_t)8 * page_size * 4 * 8 + 64 * 8 + 4 * 64 * 8 +
-                      4 * 4 * 34 * 4 + 2 * atom::DEC_STAGES * 8 + 128;
+  const size_t smem = atom::batch_decode_smem_bytes(page_size);
   if (page_size <= 32) {
     if ((rc = ensure_dynamic_smem(atom::batch_decode_kernel<4>, 100 * 1024, "batch_decode_i4"))) return rc;
   } else {

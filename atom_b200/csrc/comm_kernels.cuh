@@ -57,7 +57,16 @@ allreduce_push_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uin
   if (tid < world) {
     st_release_sys_u32(flags[tid] + ((size_t)par * gridDim.x + bid) * world + rank, e);
     const uint32_t* mine = flags[rank] + ((size_t)par * gridDim.x + bid) * world + tid;
-    while (ld_acquire_sys_u32(mine) != e) {}
+    // bounded: a peer that never arrives (crashed rank, mismatched launch sequence) traps after ~4 s instead of hanging the GPU
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 0; ld_acquire_sys_u32(mine) != e; ++spins) {
+      if ((spins & 0xFFFu) == 0xFFFu) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) asm volatile("trap;");
+      }
+    }
   }
   __syncthreads();
   // 3. local reduction in rank order

@@ -76,6 +76,17 @@ constexpr int DEC_CONSUMERS = 4;
 constexpr int DEC_THREADS = 32 * (DEC_CONSUMERS + 1);
 constexpr int DEC_STAGES = 8;
 
+// dynamic shared memory of batch_decode_kernel, in the order the kernel carves it up
+inline size_t batch_decode_smem_bytes(int page_size) {
+  return (size_t)DEC_STAGES * (136 * page_size)      // page ring: K | V | K params | V params
+         + (size_t)8 * page_size * 4 * 8             // tabh
+         + 64 * 8                                    // stepr
+         + 4 * 64 * 8                                // brk
+         + 4 * 4 * 8 * 8                             // brkh
+         + 4 * 4 * 34 * 4                            // merge
+         + 2 * DEC_STAGES * 8 + 128;                 // full / empty barriers, slack
+}
+
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
