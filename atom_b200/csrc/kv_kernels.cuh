@@ -99,7 +99,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // the factor it multiplies them with (scale / 16, exact).  w8 = w >> 8 serves q = 2, 3.
 __device__ __forceinline__ __half2 nib2x(uint32_t w, uint32_t w8, int q) {
   const uint32_t src = (q & 2) ? w8 : w;
-  const uint32_t u = (src & ((q & 1) ? 0x00F000F0u : 0x000F000Fu)) | 0x64006400u;
+  uint32_t u;      // (src & mask) | magic as ONE LOP3 (the C expression compiles to two: each can carry only one immediate)
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(u) : "r"(src), "r"((q & 1) ? 0x00F000F0u : 0x000F000Fu), "r"(0x64006400u));
   return __hsub2(*reinterpret_cast<const __half2*>(&u), __half2half2(__ushort_as_half(0x6400)));
 }
 
