@@ -386,7 +386,10 @@ int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t f
     // only runs on request.
     return (flags & ATOM_GEMM_FORCE_WIDE) ? launch_wide<kO4>(op, args, stream) : launch_tall<kO4>(op, args, stream);
   }
-  if (op.M <= 64 && !(flags & ATOM_GEMM_LEGACY_SKINNY)) return skinny_dispatch<kO4>(op, args, flags, stream);
+  // 33..64 tokens: the round-1 configuration (one CTA per SM, 8 converter warps) still measures faster than the new
+  // kernel's BN=64 instance (4096^2: 13.0-13.3 vs 15.0 us), which then only runs on request and under the fused epilogues
+  if (op.M <= 64 && !(flags & ATOM_GEMM_LEGACY_SKINNY) && (op.M <= 32 || (flags & ATOM_GEMM_FORCE_SKINNY)))
+    return skinny_dispatch<kO4>(op, args, flags, stream);
   // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not
   // cover the machine (the kernel is HBM-bound on the weights: more CTAs = more bytes in flight)
   const int64_t ch_tiles = (op.N + 127) / 128;

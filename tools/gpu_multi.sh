@@ -14,5 +14,6 @@ tail -2 $OUT/bench_n$N.err
 echo "== bench.py --gpus $N, NCCL all-reduce in the TP record"
 ATOM_B200_TP_ALLREDUCE=nccl timeout 420 $RUN --master-port 29518 bench.py --gpus $N --steps 300 --warmup 5 --no-sweep 2> $OUT/bench_n${N}_nccl.err | tee $OUT/bench_n${N}_nccl.json | cut -c1-1500
 tail -2 $OUT/bench_n${N}_nccl.err
+[ "$2" = "noref" ] && exit 0
 echo "== reference arm under torchrun (rank 0 only)"
 timeout 300 $RUN --master-port 29519 bench.py --impl reference --gpus $N --steps 20 --warmup 3 2> $OUT/bench_ref_n$N.err | tee $OUT/bench_ref_n$N.json | cut -c1-600

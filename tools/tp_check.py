@@ -75,6 +75,36 @@ with torch.cuda.stream(st):
         report(f"push_allreduce_graph_replay_{rep}", torch.equal(y, z), max_abs_diff=(y.float() - z.float()).abs().max().item())
 g = None
 
+# latency of one all-reduce of the decode step's size (batch 32 x hidden 8192 FP16 = 512 KiB): 50 chained calls in one graph
+def time_allreduce(ar, n, chain=50, reps=20):
+    xs = torch.randn(n, device=dev).half()
+    with torch.cuda.stream(st):
+        y = ar(xs.clone())
+        st.synchronize()
+        dist.barrier()
+        gg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gg, stream=st):
+            y = xs
+            for _ in range(chain):
+                y = ar(y.clone() if isinstance(ar, NcclAllReduce) else y)
+        gg.replay(); st.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            gg.replay()
+        e1.record(st); e1.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * chain)
+    t = torch.tensor([us], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gg = None
+    return round(t.item(), 2)
+
+for n in (16 * 4096, 32 * 8192):
+    tp_us, tn_us = time_allreduce(push, n), time_allreduce(nccl, n)
+    if rank == 0:
+        print(json.dumps({"allreduce_latency_us": {"numel": n, "bytes": 2 * n, "push": tp_us, "nccl_incl_one_copy": tn_us, "world": world,
+                                                   "how": "50 chained calls per CUDA graph, 20 replays, device time, max over ranks"}}), flush=True)
+
 # ---------------------------------------------------------------- 2. TP decoder layer: push vs NCCL
 hidden, inter, heads, batch, kvlen, page = 4096, 11008, 32, 16, 300, 16
 cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads, num_hidden_layers=1)
