@@ -357,7 +357,13 @@ int skinny_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t
   if (!kO4 && !(flags & ATOM_GEMM_NO_SPLITK)) {
     if (flags & ATOM_GEMM_SPLITK2) ksplit = 2;
     else if (flags & ATOM_GEMM_SPLITK4) ksplit = 4;
-    else if (groups >= 8) ksplit = tiles * 4 <= 160 ? 4 : (tiles * 2 <= 160 ? 2 : 1);
+    else if ((flags & ATOM_GEMM_SPLITK8) && bn <= 32) ksplit = 8;
+    else if (groups >= 8) {
+      // 16/32-token tiles run two CTAs per SM (296 slots): an 8-way split keeps every rank at >= 4 groups from 32 groups on
+      // and shortens the dependent chain of each CTA (the kernel is latency-, not bandwidth-bound)
+      if (bn <= 32 && groups >= 32 && tiles * 8 <= 296) ksplit = 8;
+      else ksplit = tiles * 4 <= 160 ? 4 : (tiles * 2 <= 160 ? 2 : 1);
+    }
   }
   if constexpr (kO4) {
     if (bn == 16) return launch_skinny<16, 1, kEpi>(op, args, stream);
@@ -368,8 +374,8 @@ int skinny_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t
   return ksplit == 4   ? launch_skinny<BN_, 4, kEpi>(op, args, stream)               \
          : ksplit == 2 ? launch_skinny<BN_, 2, kEpi>(op, args, stream)               \
                        : launch_skinny<BN_, 1, kEpi>(op, args, stream)
-    if (bn == 16) { ATOM_SK(16); }
-    if (bn == 32) { ATOM_SK(32); }
+    if (bn == 16) { if (ksplit == 8) return launch_skinny<16, 8, kEpi>(op, args, stream); ATOM_SK(16); }
+    if (bn == 32) { if (ksplit == 8) return launch_skinny<32, 8, kEpi>(op, args, stream); ATOM_SK(32); }
     ATOM_SK(64);
 #undef ATOM_SK
   }
@@ -377,7 +383,9 @@ int skinny_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t
 
 template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
-  const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 64);
+  // up to 128 tokens the weight-stationary orientation wins (4096^2, M=128: 13.9 us as two 64-token tiles vs 21.3 us for one
+  // wave of 32 128x128 tiles); from 3 token tiles on the 128x128 kernel is faster
+  const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 128);
   // <swap, BN, groups per pipeline stage, packed stages, K split, o4, converter warps, epilogue warpgroups>
   if (!skinny) {
     if (flags & ATOM_GEMM_LEGACY_TALL) return launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream);

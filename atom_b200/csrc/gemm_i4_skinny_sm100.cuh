@@ -73,7 +73,7 @@ struct SkinnyCfg {
   static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
   static constexpr int CTAS_PER_SM = ONE_PER_SM ? 1 : 2;
   static_assert(BN == 16 || BN == 32 || BN == 64, "token tile");
-  static_assert(BN % kSplit == 0 && CPR >= 4, "every split-K rank owns at least 4 token columns");
+  static_assert(BN % kSplit == 0 && CPR >= 2, "every split-K rank owns at least 2 token columns (one 8-byte st.async)");
   static_assert(kEpi == EPI_O16 || (kEpi == EPI_GATEUP && kSplit == 2) || kSplit == 1, "the quantising epilogues work on un-split FP32 sums");
   static_assert(A_PAIRS * 64 + ACC_PAIRS * 2 * BN <= TMEM_COLS, "tensor memory budget");
   static_assert(A_PAIRS >= ACC_PAIRS, "mma_done is indexed by operand slot");
@@ -105,6 +105,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float b, float c, float d, uint32_t remote_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(remote_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar) : "memory");
+}
+
+__device__ __forceinline__ void st_async_v2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "r"(remote_bar) : "memory");
 }
 
 // 16 token columns of one group: acc[c] = fmaf(float(c_int), float(hmul(sA[c], sB)), acc[c]).  Token c with c%16 < 8 pairs
@@ -152,9 +157,9 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   if constexpr (kSplit > 1) {
     krank = cluster_ctarank();
     if constexpr (kEpi != EPI_GATEUP) {
-      const int per = (total_groups + kSplit - 1) / kSplit;
-      g_begin = min((int)krank * per, total_groups);
-      g_end = min(g_begin + per, total_groups);
+      // balanced K ranges (33 groups over 8 ranks: 4,4,4,4,4,4,4,5 -- the cheap keeper group goes to the last rank)
+      g_begin = (int)krank * total_groups / kSplit;
+      g_end = ((int)krank + 1) * total_groups / kSplit;
     }
   }
   // gate/up: the two ranks are not K slices but the gate (rank 0) and up (rank 1) rows of the same channel tile
@@ -522,10 +527,14 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
             const int slot_in_dst = (int)krank < d ? (int)krank : (int)krank - 1;
             const uint32_t remote = mapa_shared(red_local, d) + slot_in_dst * C::RED_BYTES + row * (C::CPR * 4);
             const uint32_t rbar = mapa_shared(bar_local, d);
+            if constexpr (C::CPR == 2) {
+              st_async_v2(remote, acc[d * 2], acc[d * 2 + 1], rbar);
+            } else {
 #pragma unroll
-            for (int c = 0; c < C::CPR; c += 4)
-              st_async_v4(remote + c * 4, acc[d * C::CPR + c], acc[d * C::CPR + c + 1], acc[d * C::CPR + c + 2],
-                          acc[d * C::CPR + c + 3], rbar);
+              for (int c = 0; c < C::CPR; c += 4)
+                st_async_v4(remote + c * 4, acc[d * C::CPR + c], acc[d * C::CPR + c + 1], acc[d * C::CPR + c + 2],
+                            acc[d * C::CPR + c + 3], rbar);
+            }
           }
         }
         mbar_wait(red_full, 0);

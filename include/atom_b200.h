@@ -42,6 +42,7 @@ extern "C" {
 #define ATOM_GEMM_FORCE_SKINNY 4u /* channels on the MMA-M axis (requires M <= 128 per tile; any M works) */
 #define ATOM_GEMM_SPLITK2 16u     /* decode shapes: force a 2-way K split (default: chosen from the tile count) */
 #define ATOM_GEMM_SPLITK4 32u     /* decode shapes: force a 4-way K split */
+#define ATOM_GEMM_SPLITK8 64u     /* decode shapes, M <= 32: force an 8-way K split (cluster of 8) */
 #define ATOM_GEMM_FORCE_WIDE 512u    /* prefill shapes: 128 x 256 tiles, token operand in tensor memory (opt-in: measured slower than 128 x 128) */
 #define ATOM_GEMM_NO_WIDE 1024u      /* prefill shapes: always 128 x 128 tiles (the default; kept for callers that pass it) */
 #define ATOM_GEMM_LEGACY_TALL 256u   /* prefill shapes: the round-1 kernel (I2F + FFMA epilogue), kept for A/B timing */
@@ -83,7 +84,7 @@ ATOM_API int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, in
  *   a_keeper i8 [M,128] b_keeper i8 [N,128] a_keeper_scale f16 [scale_size(M)]    b_keeper_scale f16 [N]
  *   d f16 [M,N].   K includes the 128 keeper channels (as in the e2e launcher).  N % 8 == 0, K % 128 == 0, K >= 256.
  * Bit-identity: every path accumulates the groups in the reference's order (0..G-1, keeper last) and is bit-identical to the
- * reference kernel, EXCEPT flags = ATOM_GEMM_AUTO with M <= 64 when the dispatcher splits K over a cluster (channel tiles
+ * reference kernel, EXCEPT flags = ATOM_GEMM_AUTO with M <= 128 when the dispatcher splits K over a cluster (channel tiles
  * alone would not fill the GPU): the FP32 partials are then summed per K slice, <= 1 fp16 ulp on < 2 % of the outputs (inside
  * the operator's 1e-3 contract).  ATOM_GEMM_NO_SPLITK restores the reference's order at decode sizes.
  * The weights (b, b_scale, b_keeper, b_keeper_scale) are read before the preceding kernel on `stream` has completed

@@ -110,7 +110,7 @@ GEMM_CASES = [
     (16, 256, 512, 5, True), (7, 128, 384, 5, True), (1, 128, 256, 5, True), (33, 256, 1024, 5, True),
     (64, 384, 4096, 5, True), (16, 4096, 4096, 1, True),
     (16, 4096, 4096, 0, False), (32, 1024, 4096, 0, False), (48, 512, 11008, 0, False), (5, 128, 2048, 0, False),
-    (130, 2752, 1024, 0, True),
+    (130, 2752, 1024, 0, True), (100, 256, 2048, 0, False), (128, 512, 512, 1, True), (65, 1024, 4096, 1, True),
     # 512 = 128 x 256 tiles with the token operand in tensor memory (the default once such tiles fill the GPU): N % 256 != 0
     # (one-half last tile, partially filled second half), M tails, long K
     (300, 256, 4096, 512, True), (129, 384, 1024, 512, True), (130, 2752, 1024, 512, True), (7, 512, 384, 512, True),

@@ -55,7 +55,7 @@ def test_activate_equals_reference_kernel(m):
     _cmp_quant(ops.activate_fp16_i4(a, b), R.activate_fp16_i4(a, b), m)
 
 
-@pytest.mark.parametrize("m,n,k,flags", [(16, 4096, 4096, 1), (7, 4096, 4096, 1), (128, 4096, 4096, 0), (1000, 4096, 4096, 0),
+@pytest.mark.parametrize("m,n,k,flags", [(16, 4096, 4096, 1), (7, 4096, 4096, 1), (128, 4096, 4096, 1), (128, 4096, 4096, 2), (1000, 4096, 4096, 0),
                                          (4096, 4096, 4096, 0), (16, 11008, 4096, 1), (33, 4096, 11008, 1), (300, 4096, 11008, 0),
                                          # Llama-13B (config #4) and Llama-65B TP-8 (config #5) projection shapes, decode batch 32
                                          (32, 5120, 5120, 1), (32, 13824, 5120, 1), (32, 5120, 13824, 1), (32, 1024, 8192, 1),
