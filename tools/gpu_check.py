@@ -251,7 +251,7 @@ if __name__ == "__main__":
             nrot = max(3, int(300e6 // per_set) + 1)
             sets = [[T(x) for x in base] for _ in range(nrot)]
             rec = {"gshape": [m, n, k]}
-            for name, flags in {"auto": 0, "nosplit": 1, "split2": 16, "split4": 32, "legacy_auto": 128}.items():
+            for name, flags in {"auto": 0, "nosplit": 1, "split2": 16, "split4": 32, "split8": 64, "legacy_auto": 128}.items():
                 us = graph_time(lambda i: ops.dense_layer_gemm_i4_fp16(*sets[i % nrot], flags=flags), nrot, launches=nrot)
                 rec[name] = round(us, 2)
             print(json.dumps(rec), flush=True)
