@@ -28,7 +28,8 @@ _SIGNATURES = {
     "atom_set_pdl": (_I, [_I]),
     "atom_batch_decode_i4": (_I, [_P] * 7 + [_I] * 5 + [_P]),
     "atom_prefill_attention_i4": (_I, [_P] * 11 + [_I] * 4 + [_P]),
-    "atom_allreduce_push_f16": (_I, [_P] * 5 + [_I64, _I64, _I, _I, _P]),
+    "atom_allreduce_push_f16": (_I, [_P] * 4 + [_I64, _I64, _I, _I, _P]),
+    "atom_allreduce_state_words": (_I, []),
     "atom_append_kv_i4": (_I, [_P] * 9 + [_I] * 5 + [_P]),
     "atom_init_kv_i4": (_I, [_P] * 10 + [_I] * 6 + [_P]),
 }

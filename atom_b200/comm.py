@@ -3,7 +3,8 @@ multi-GPU code.
 
 `PushAllReduce` is the latency-oriented all-reduce of the row-parallel projections: a hand-written one-shot kernel
 (csrc/comm_kernels.cuh) that pushes every rank's FP16 partial into all peers' receive buffers over NVLink peer mappings
-and reduces locally -- one launch, no closing barrier, CUDA-graph capturable.  The peer mappings come from
+and reduces locally as the payload arrives (sentinel-filled rotating buffers: no flags, no fence, no barrier) -- one
+launch, CUDA-graph capturable.  The peer mappings come from
 torch.distributed._symmetric_memory (plumbing only: allocation + pointer exchange).  `make_allreduce` falls back to
 ncclAllReduce (torch.distributed.all_reduce) when symmetric memory cannot be set up, and says which one it returned.
 """
@@ -38,15 +39,12 @@ class PushAllReduce:
         name = group.group_name
         if hasattr(symm_mem, "is_symm_mem_enabled_for_group") and not symm_mem.is_symm_mem_enabled_for_group(name):
             symm_mem.enable_symm_mem_for_group(name)
-        self.buf = symm_mem.empty(2 * self.world * self.slot, dtype=torch.float16, device=device)
-        self.flags = symm_mem.empty(2 * self.CTAS * self.world, dtype=torch.int32, device=device)
-        self.buf.zero_()
-        self.flags.zero_()
+        self.buf = symm_mem.empty(3 * self.world * self.slot, dtype=torch.float16, device=device)
+        self.buf.view(torch.int16).fill_(-32768)          # 0x8000 = FP16 -0.0: "not yet arrived"
         self.hbuf = symm_mem.rendezvous(self.buf, group)
-        self.hflags = symm_mem.rendezvous(self.flags, group)
-        self.epoch = torch.zeros(self.CTAS, dtype=torch.int32, device=device)
+        self.state = torch.zeros(_lib.lib().atom_allreduce_state_words(), dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
-        dist.barrier(group)                  # every rank's buffers are zeroed and mapped before anybody pushes
+        dist.barrier(group)                  # every rank's buffers are initialised and mapped before anybody pushes
 
     def __call__(self, x):
         if x.dtype != torch.float16 or not x.is_contiguous() or x.numel() % 8 or x.numel() > self.slot:
@@ -54,7 +52,7 @@ class PushAllReduce:
         out = torch.empty_like(x)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().atom_allreduce_push_f16(x.data_ptr(), out.data_ptr(), self.hbuf.buffer_ptrs_dev,
-                                                          self.hflags.buffer_ptrs_dev, self.epoch.data_ptr(), x.numel(), self.slot,
+                                                          self.state.data_ptr(), x.numel(), self.slot,
                                                           self.rank, self.world, torch.cuda.current_stream(x.device).cuda_stream),
                        "allreduce_push_f16")
         return out

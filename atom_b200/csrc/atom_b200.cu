@@ -620,18 +620,19 @@ int atom_prefill_attention_i4(const void* q, const void* k, const void* k_param,
   return check_launch("prefill_attention_i4");
 }
 
-int atom_allreduce_push_f16(const void* in, void* out, const void* peer_buffers, const void* peer_flags, void* epoch,
-                            int64_t numel, int64_t slot_elems, int rank, int world, void* stream) {
-  ATOM_REQUIRE(in && out && peer_buffers && peer_flags && epoch, "allreduce_push_f16: null pointer argument");
+int atom_allreduce_push_f16(const void* in, void* out, const void* peer_buffers, void* state, int64_t numel, int64_t slot_elems,
+                            int rank, int world, void* stream) {
+  ATOM_REQUIRE(in && out && peer_buffers && state, "allreduce_push_f16: null pointer argument");
   ATOM_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "allreduce_push_f16: rank=%d world=%d", rank, world);
   ATOM_REQUIRE(numel > 0 && numel % 8 == 0 && numel <= slot_elems && slot_elems % 8 == 0,
                "allreduce_push_f16: numel=%lld must be a positive multiple of 8 and fit a slot of %lld elements", (long long)numel, (long long)slot_elems);
   ATOM_REQUIRE(aligned16(in) && aligned16(out), "allreduce_push_f16: in / out must be 16-byte aligned");
   atom::allreduce_push_kernel<<<atom::AR_CTAS, atom::AR_THREADS, 0, (cudaStream_t)stream>>>(
-      (const uint4*)in, (uint4*)out, (uint4* const*)peer_buffers, (uint32_t* const*)peer_flags, (uint32_t*)epoch, numel / 8,
-      slot_elems / 8, rank, world);
+      (const uint4*)in, (uint4*)out, (uint4* const*)peer_buffers, (uint32_t*)state, numel / 8, slot_elems / 8, rank, world);
   return check_launch("allreduce_push_f16");
 }
+
+int atom_allreduce_state_words(void) { return atom::AR_STATE_WORDS; }
 
 static int kv_check(const char* what, const void* data, const void* param, const void* indptr, const void* indices,
                     const void* last, int L, int layer, int H, int P, int B) {

@@ -2,81 +2,93 @@
 //
 // The row-parallel projections (o_proj, down_proj) of a decode step leave an FP16 [batch, hidden] partial on every rank
 // (512 KiB at Llama-65B, batch 32) that must be summed across the ranks: a latency-bound collective.
-// The reference has no multi-GPU code at all; round 1 called ncclAllReduce.  This kernel does the exchange itself:
-//   1. every CTA pushes its slice of the local partial into slot [parity][my rank] of EVERY rank's receive buffer (plain
-//      16-byte stores through the NVLink peer mappings: fire and forget, no read round trip),
-//   2. fences, raises one flag per peer (st.release.sys) and waits for the peers' flags of the same CTA index
-//      (ld.acquire.sys on local memory),
-//   3. sums the `world` slots of its slice from LOCAL memory in rank order (FP32, identical on every rank) and writes the
-//      FP16 result.
-// Receive buffers and flags are double-buffered by the parity of a device-side epoch counter, which makes a closing
-// barrier unnecessary (a rank can only reach epoch e+2 after every peer has signalled e+1, i.e. finished reading e) and
-// keeps the kernel CUDA-graph capturable: no host-side state changes between replays.
+// The reference has no multi-GPU code at all; round 1 called ncclAllReduce.  This kernel does the exchange itself, with
+// no flag round trip and no fence (Lamport-style: the payload is its own arrival signal):
+//   1. every CTA pushes its slice of the local partial into slot [e % 3][my rank] of EVERY rank's receive buffer (plain
+//      16-byte stores through the NVLink peer mappings: fire and forget).  Receive buffers are pre-filled with a sentinel
+//      bit pattern (FP16 -0.0 = 0x8000) that the payload never contains: a -0.0 input is sent as +0.0, which leaves every
+//      sum unchanged except that an all-(-0.0) column yields +0.0;
+//   2. it resets ITS OWN buffer [(e + 2) % 3] -- the one read in the previous call -- to the sentinel for a later call;
+//   3. it polls the `world` slots of its slice in LOCAL memory until no 16-byte chunk holds a sentinel half (a torn write
+//      just keeps it polling), sums them in rank order in FP32 (identical on every rank) and writes the FP16 result.
+// Three buffers rotate on a device-side epoch counter, so the kernel is CUDA-graph capturable and needs no barrier: a peer
+// can write buffer e % 3 again only in call e + 3, which it reaches after my push of call e + 2, i.e. after I finished
+// call e; and buffer (e + 2) % 3 is not written by anybody before call e + 2, which every peer reaches only after my push
+// of call e + 1, i.e. after the reset of call e completed (kernel boundary).
+// An earlier revision (fence + one flag per peer + acquire spin) measured 24.6 us for 512 KiB over 8 GPUs against 31.6 us
+// for ncclAllReduce (profiles/r02_tp_check_n8.jsonl).
 #pragma once
 #include "ptx_sm100.cuh"
 
 namespace atom {
 
 constexpr int AR_CTAS = 64, AR_THREADS = 256;
+constexpr int AR_STATE_WORDS = AR_CTAS + 4;     // epoch per CTA, then the chunk count last written into each of the 3 buffers
 
-__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
   uint4 v;
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_volatile_v4(void* p, const uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// FP16 -0.0 (0x8000) in either half of w
+__device__ __forceinline__ bool has_sentinel(uint32_t w) { return (w & 0xFFFFu) == 0x8000u || (w >> 16) == 0x8000u; }
+__device__ __forceinline__ uint32_t strip_sentinel(uint32_t w) {
+  if ((w & 0xFFFFu) == 0x8000u) w &= 0xFFFF0000u;
+  if ((w >> 16) == 0x8000u) w &= 0x0000FFFFu;
+  return w;
+}
 
-// in, out: f16 [numel] local; bufs[r]: rank r's receive buffer, f16 [2][world][slot_elems]; flags[r]: u32 [2][AR_CTAS][world];
-// epoch: u32 [AR_CTAS] local, zero-initialised once.  numel % 8 == 0, numel <= slot_elems.
+// in, out: f16 [numel] local; bufs[r]: rank r's receive buffer, f16 [3][world][slot_elems], filled with 0x8000 once;
+// state: u32 [AR_STATE_WORDS] local, zeroed once.  numel % 8 == 0, numel <= slot_elems.
 __global__ void __launch_bounds__(AR_THREADS)
-allreduce_push_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint4* const* __restrict__ bufs,
-                      uint32_t* const* __restrict__ flags, uint32_t* __restrict__ epoch, long long nchunks, long long slot_chunks,
-                      int rank, int world) {
-  __shared__ uint32_t e_s;
+allreduce_push_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint4* const* __restrict__ bufs, uint32_t* __restrict__ state,
+                      long long nchunks, long long slot_chunks, int rank, int world) {
+  __shared__ uint32_t e_s, last_s;
   const int tid = threadIdx.x, bid = blockIdx.x;
-  if (tid == 0) e_s = epoch[bid] + 1;
+  if (tid == 0) { e_s = state[bid] + 1; last_s = state[AR_CTAS + (e_s + 2) % 3]; }
   __syncthreads();
-  const uint32_t e = e_s, par = e & 1u;
+  const uint32_t e = e_s, cur = e % 3, clr = (e + 2) % 3;
   const long long per = (nchunks + gridDim.x - 1) / gridDim.x;
   const long long lo = min((long long)bid * per, nchunks), hi = min(lo + per, nchunks);
-  // 1. push my slice into slot [par][rank] of every rank (my own included: the reduction below is then uniform)
+  // 1. push my slice into slot [cur][rank] of every rank (my own included: the reduction below is then uniform)
   for (long long i = lo + tid; i < hi; i += AR_THREADS) {
-    const uint4 v = in[i];
-    for (int r = 0; r < world; ++r) bufs[r][((long long)par * world + rank) * slot_chunks + i] = v;
+    uint4 v = in[i];
+    v.x = strip_sentinel(v.x); v.y = strip_sentinel(v.y); v.z = strip_sentinel(v.z); v.w = strip_sentinel(v.w);
+    for (int r = 0; r < world; ++r)      // destinations staggered by rank: no two ranks start on the same peer
+      st_volatile_v4(bufs[(rank + r) % world] + ((long long)cur * world + rank) * slot_chunks + i, v);
   }
-  __threadfence_system();
-  __syncthreads();
-  // 2. one flag per peer; wait for the same CTA of every peer
-  if (tid < world) {
-    st_release_sys_u32(flags[tid] + ((size_t)par * gridDim.x + bid) * world + rank, e);
-    const uint32_t* mine = flags[rank] + ((size_t)par * gridDim.x + bid) * world + tid;
-    // bounded: a peer that never arrives (crashed rank, mismatched launch sequence) traps after ~4 s instead of hanging the GPU
-    unsigned long long t0 = 0;
-    for (uint32_t spins = 0; ld_acquire_sys_u32(mine) != e; ++spins) {
-      if ((spins & 0xFFFu) == 0xFFFu) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000ull) asm volatile("trap;");
-      }
-    }
+  // 2. reset the buffer of the previous call: whatever was written into it (possibly a longer message than this one)
+  {
+    const long long cchunks = max((long long)last_s, 0ll);
+    const long long cper = (cchunks + gridDim.x - 1) / gridDim.x;
+    const long long clo = min((long long)bid * cper, cchunks), chi = min(clo + cper, cchunks);
+    const uint4 sv = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+    uint4* base = bufs[rank] + (long long)clr * world * slot_chunks;
+    for (int r = 0; r < world; ++r)
+      for (long long i = clo + tid; i < chi; i += AR_THREADS) base[(long long)r * slot_chunks + i] = sv;
   }
-  __syncthreads();
-  // 3. local reduction in rank order
-  const uint4* local = bufs[rank] + (long long)par * world * slot_chunks;
+  // 3. poll + reduce in rank order from local memory
+  const uint4* local = bufs[rank] + (long long)cur * world * slot_chunks;
+  unsigned long long t0 = 0;
   for (long long i = lo + tid; i < hi; i += AR_THREADS) {
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     for (int r = 0; r < world; ++r) {
-      const uint4 v = ld_volatile_v4(local + (long long)r * slot_chunks + i);     // written remotely: do not trust L1
+      uint4 v = ld_volatile_v4(local + (long long)r * slot_chunks + i);     // written remotely: do not trust L1
+      // bounded: a peer that never arrives (crashed rank, mismatched call sequence) traps after ~4 s instead of hanging the GPU
+      for (uint32_t spins = 0; has_sentinel(v.x) || has_sentinel(v.y) || has_sentinel(v.z) || has_sentinel(v.w); ++spins) {
+        if ((spins & 0x3FFu) == 0x3FFu) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 4000000000ull) asm volatile("trap;");
+        }
+        v = ld_volatile_v4(local + (long long)r * slot_chunks + i);
+      }
       const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
       for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
@@ -87,7 +99,10 @@ allreduce_push_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uin
     for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
     out[i] = o;
   }
-  if (tid == 0) epoch[bid] = e;
+  if (tid == 0) {
+    state[bid] = e;
+    if (bid == 0) state[AR_CTAS + cur] = (uint32_t)nchunks;     // read again (as `last`) by call e + 1, a later kernel
+  }
 }
 
 }  // namespace atom

@@ -149,12 +149,15 @@ ATOM_API int atom_prefill_attention_i4(const void* q, const void* k, const void*
                               void* out, int total_tokens, int batch_size, int max_len, int num_heads, void* stream);
 
 /* EXTENSION (the reference has no multi-GPU code): one-shot all-reduce (sum) of an FP16 vector over NVLink peer
- * memory for the tensor-parallel row-parallel projections.  peer_buffers / peer_flags: DEVICE arrays of `world` pointers
- * to every rank's receive buffer (f16 [2][world][slot_elems]) and flag block (u32 [2][64][world], zeroed once), e.g. from
- * torch.distributed._symmetric_memory; epoch: local u32 [64], zeroed once.  Every rank must make the same sequence of calls.
+ * memory for the tensor-parallel row-parallel projections.  peer_buffers: DEVICE array of `world` pointers to every rank's
+ * receive buffer, f16 [3][world][slot_elems], every half initialised to 0x8000 (FP16 -0.0: the "not yet arrived" pattern;
+ * a -0.0 input element is transmitted as +0.0), e.g. allocated and exchanged with torch.distributed._symmetric_memory;
+ * state: local u32 [atom_allreduce_state_words()], zeroed once.  Every rank must make the same sequence of calls.
+ * No flags, fences or barriers: the payload is its own arrival signal (three rotating buffers on a device-side call counter).
  * Graph-capturable; the sum is formed in rank order in FP32 and is bit-identical on all ranks. */
-ATOM_API int atom_allreduce_push_f16(const void* in, void* out, const void* peer_buffers, const void* peer_flags, void* epoch,
-                            int64_t numel, int64_t slot_elems, int rank, int world, void* stream);
+ATOM_API int atom_allreduce_push_f16(const void* in, void* out, const void* peer_buffers, void* state, int64_t numel,
+                            int64_t slot_elems, int rank, int world, void* stream);
+ATOM_API int atom_allreduce_state_words(void);
 
 /* replaces append_kv_i4 (punica_ops.cc:166-209 -> FlashInferAppendKvKernel_i4<128>, flashinfer_impl.cuh:73-96)
  *   k,v u8 [B,H,64]  k_param,v_param f16 [B,H,2] */

@@ -1,7 +1,8 @@
-"""The push all-reduce kernel (csrc/comm_kernels.cuh) on ONE GPU: with world == 1 the "peer" tables hold the local buffers,
-so the full protocol runs (push into slot [parity][0], flag raise + wait, FP32 reduction, epoch advance) and the result must
-equal the input bit for bit -- eagerly, with sizes that leave CTAs without work, and across CUDA-graph replays (the parity
-double-buffering is driven by the device-side epoch).  The N >= 2 behaviour is covered by tools/tp_check.py under torchrun
+"""The push all-reduce kernel (csrc/comm_kernels.cuh) on ONE GPU: with world == 1 the "peer" table holds the local buffer,
+so the full protocol runs (push into slot [e % 3][0], reset of the previous buffer to the sentinel, poll, FP32 reduction,
+call counter) and the result must equal the input bit for bit (-0.0 arrives as +0.0) -- eagerly, with sizes that grow and
+shrink between calls and leave CTAs without work, and across CUDA-graph replays (the buffer rotation is driven by the
+device-side counter).  The N >= 2 behaviour is covered by tools/tp_check.py under torchrun
 (profiles/r02_tp_check_n{2,8}.jsonl) and the host logic by tests/test_tp_gloo.py."""
 import pytest
 import torch
@@ -12,17 +13,15 @@ pytestmark = pytest.mark.gpu
 
 
 def _setup(slot, dev):
-    buf = torch.zeros(2 * 1 * slot, dtype=torch.float16, device=dev)          # [parity][world=1][slot]
-    flags = torch.zeros(2 * 64 * 1, dtype=torch.int32, device=dev)            # [parity][AR_CTAS][world]
-    epoch = torch.zeros(64, dtype=torch.int32, device=dev)
+    buf = torch.full((3 * 1 * slot,), -32768, dtype=torch.int16, device=dev)  # [3][world=1][slot] of 0x8000 (FP16 -0.0)
+    state = torch.zeros(_lib.lib().atom_allreduce_state_words(), dtype=torch.int32, device=dev)
     bufs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=dev)
-    flgs = torch.tensor([flags.data_ptr()], dtype=torch.int64, device=dev)
-    return buf, flags, epoch, bufs, flgs
+    return buf, state, bufs
 
 
 def _call(x, out, st, slot):
-    buf, flags, epoch, bufs, flgs = st
-    _lib.check(_lib.lib().atom_allreduce_push_f16(x.data_ptr(), out.data_ptr(), bufs.data_ptr(), flgs.data_ptr(), epoch.data_ptr(),
+    buf, state, bufs = st
+    _lib.check(_lib.lib().atom_allreduce_push_f16(x.data_ptr(), out.data_ptr(), bufs.data_ptr(), state.data_ptr(),
                                                   x.numel(), slot, 0, 1, torch.cuda.current_stream().cuda_stream), "allreduce_push_f16")
 
 
@@ -30,14 +29,21 @@ def test_world1_identity_and_epochs():
     dev = torch.device("cuda", 0)
     slot = 32 * 8192
     st = _setup(slot, dev)
-    for it, n in enumerate([8, 64, 4096, 32 * 5120, slot, 2048, slot]):
+    for it, n in enumerate([8, 64, 4096, 32 * 5120, slot, 2048, slot, 8, slot]):
         torch.manual_seed(it)
         x = (torch.randn(n, device=dev) * 5).half()
-        out = torch.empty_like(x)
+        x[::7] = -0.0                                           # the sentinel pattern as payload: must arrive as +0.0
+        x[3::11] = 0.0
+        out = torch.full_like(x, 7.0)
         _call(x, out, st, slot)
         torch.cuda.synchronize()
-        assert torch.equal(out, x), f"call {it} (numel {n})"
-    assert int(st[2].max()) == 7 and int(st[2].min()) == 7      # every CTA advanced its epoch once per call
+        assert torch.equal(out, x), f"call {it} (numel {n})"   # (-0.0 == +0.0 under torch.equal)
+        assert not (out.view(torch.int16) == -32768).any(), "-0.0 must be delivered as +0.0"
+    assert int(st[1][:64].max()) == 9 and int(st[1][:64].min()) == 9      # every CTA counted every call
+    torch.cuda.synchronize()
+    # after the last call only the buffer it used holds payload; the one before it has been reset
+    b3 = st[0].view(3, slot)
+    assert (b3[(9 + 2) % 3] == -32768).all()
 
 
 def test_world1_graph_replay():
