@@ -30,6 +30,8 @@ _SIGNATURES = {
     "atom_prefill_attention_i4": (_I, [_P] * 11 + [_I] * 4 + [_P]),
     "atom_allreduce_push_f16": (_I, [_P] * 4 + [_I64, _I64, _I, _I, _P]),
     "atom_allreduce_state_words": (_I, []),
+    "atom_gemm_i4_o16_push": (_I, [_P] * 10 + [_I64, _I, _I, _I64, _I64, _I64, _U32, _P]),
+    "atom_reduce_add_rmsnorm_fp16_i4": (_I, [_P, _P, _I64, _I, _I, _P, _P, _P, _F, _P, _I, _I, _P, _P, _P, _P, _P]),
     "atom_append_kv_i4": (_I, [_P] * 9 + [_I] * 5 + [_P]),
     "atom_init_kv_i4": (_I, [_P] * 10 + [_I] * 6 + [_P]),
 }

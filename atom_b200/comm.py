@@ -45,6 +45,9 @@ class PushAllReduce:
         self.state = torch.zeros(_lib.lib().atom_allreduce_state_words(), dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group)                  # every rank's buffers are initialised and mapped before anybody pushes
+        from .ops import ArHandle
+        # for the fused entry points (ops.dense_layer_gemm_i4_fp16_push / reduce_add_rmsnorm_fp16_i4): same buffers, same counter
+        self.handle = ArHandle(self.hbuf.buffer_ptrs_dev, self.state, self.slot, self.rank, self.world)
 
     def __call__(self, x):
         if x.dtype != torch.float16 or not x.is_contiguous() or x.numel() % 8 or x.numel() > self.slot:

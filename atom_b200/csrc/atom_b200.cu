@@ -344,9 +344,9 @@ int launch_wide(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
   return ATOM_OK;
 }
 
-template <bool kO4>
+template <bool kO4, bool kPush = false>
 int skinny_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
-  constexpr int kEpi = kO4 ? atom::EPI_O4 : atom::EPI_O16;
+  constexpr int kEpi = kO4 ? atom::EPI_O4 : (kPush ? atom::EPI_PUSH : atom::EPI_O16);
   const int64_t ch_tiles = (op.N + 127) / 128;
   const int groups = args.G + 1;
   const int bn = op.M <= 16 ? 16 : (op.M <= 32 ? 32 : 64);
@@ -359,10 +359,13 @@ int skinny_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t
     else if (flags & ATOM_GEMM_SPLITK4) ksplit = 4;
     else if ((flags & ATOM_GEMM_SPLITK8) && bn <= 32) ksplit = 8;
     else if (groups >= 8) {
-      // 16/32-token tiles run two CTAs per SM (296 slots): an 8-way split keeps every rank at >= 4 groups from 32 groups on
-      // and shortens the dependent chain of each CTA (the kernel is latency-, not bandwidth-bound)
-      if (bn <= 32 && groups >= 32 && tiles * 8 <= 296) ksplit = 8;
-      else ksplit = tiles * 4 <= 160 ? 4 : (tiles * 2 <= 160 ? 2 : 1);
+      // The kernel is latency-, not bandwidth-bound: the largest split whose CTAs are all resident at once wins (148 SMs, two
+      // CTAs each for the 16/32-token tiles), as long as every rank keeps >= 4 groups (8-way: from 32 groups on).
+      // Measured (r02_gemm_skinny_v8_shape_table.jsonl): 16x4096x4096 5.9 us at 8 vs 6.3 at 4; 16x11008x4096 10.3 at 2 vs 12.6 at 1
+      // and 12.9 at 4 (344 CTAs: a second wave); 32x13824x5120 19.1 at 2 vs 29.0 at 1.
+      const int64_t slots = bn <= 32 ? 296 : 160;
+      if (bn <= 32 && groups >= 32 && tiles * 8 <= slots) ksplit = 8;
+      else ksplit = tiles * 4 <= slots ? 4 : (tiles * 2 <= slots ? 2 : 1);
     }
   }
   if constexpr (kO4) {
@@ -396,8 +399,10 @@ int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t f
   }
   // 33..64 tokens: the round-1 configuration (one CTA per SM, 8 converter warps) still measures faster than the new
   // kernel's BN=64 instance (4096^2: 13.0-13.3 vs 15.0 us), which then only runs on request and under the fused epilogues
-  if (op.M <= 64 && !(flags & ATOM_GEMM_LEGACY_SKINNY) && (op.M <= 32 || (flags & ATOM_GEMM_FORCE_SKINNY)))
+  if (op.M <= 64 && !(flags & ATOM_GEMM_LEGACY_SKINNY) && (op.M <= 32 || (flags & ATOM_GEMM_FORCE_SKINNY))) {
+    if constexpr (!kO4) { if (args.ar.bufs != nullptr) return skinny_dispatch<false, true>(op, args, flags, stream); }
     return skinny_dispatch<kO4>(op, args, flags, stream);
+  }
   // decode shapes: weights on the MMA-M axis; K split 4-way over a cluster when one wave of CTAs would not
   // cover the machine (the kernel is HBM-bound on the weights: more CTAs = more bytes in flight)
   const int64_t ch_tiles = (op.N + 127) / 128;
@@ -425,8 +430,8 @@ int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t f
 
 int gemm_common(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
                 const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, void* d, void* d_scale,
-                int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream, bool o4) {
-  ATOM_REQUIRE(a && b && a_scale && b_scale && a_keeper && b_keeper && a_keeper_scale && b_keeper_scale && d,
+                int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream, bool o4, const atom::ArArgs* ar = nullptr) {
+  ATOM_REQUIRE(a && b && a_scale && b_scale && a_keeper && b_keeper && a_keeper_scale && b_keeper_scale && (d || ar),
                "gemm_i4: null pointer argument");
   ATOM_REQUIRE(M > 0 && N > 0, "gemm_i4: M=%lld N=%lld must be positive", (long long)M, (long long)N);
   ATOM_REQUIRE(K >= 256 && K % 128 == 0, "gemm_i4: K=%lld must be a multiple of 128 and >= 256 (INT4 groups + 128 keeper)", (long long)K);
@@ -434,6 +439,13 @@ int gemm_common(const void* a, const void* b, const void* a_scale, const void* b
   ATOM_REQUIRE(!o4 || (N % 128 == 0 && d_scale), "gemm_i4_o4: N=%lld must be a multiple of 128 (one head per scale)", (long long)N);
   ATOM_REQUIRE(aligned16(a) && aligned16(b) && aligned16(a_keeper) && aligned16(b_keeper) && aligned16(d),
                "gemm_i4: operand pointers must be 16-byte aligned");
+  if (ar != nullptr) {
+    ATOM_REQUIRE(!o4 && M <= 64, "gemm_i4_o16_push: decode batches only (M=%lld <= 64), fp16 output", (long long)M);
+    ATOM_REQUIRE(ar->bufs && ar->state && ar->world >= 1 && ar->world <= 32 && ar->rank >= 0 && ar->rank < ar->world && ar->slot % 8 == 0 &&
+                 M * N <= ar->slot, "gemm_i4_o16_push: rank=%d world=%d, M x N = %lld must fit a slot of %lld elements", ar->rank, ar->world,
+                 (long long)(M * N), (long long)ar->slot);
+    flags = (flags | ATOM_GEMM_FORCE_SKINNY) & ~(ATOM_GEMM_FORCE_TALL | ATOM_GEMM_LEGACY_SKINNY);
+  }
   ATOM_REQUIRE(aligned16(b_scale) && aligned16(b_keeper_scale), "gemm_i4: weight scale pointers must be 16-byte aligned");
   ATOM_REQUIRE((reinterpret_cast<uintptr_t>(a_scale) & 3) == 0 && (reinterpret_cast<uintptr_t>(a_keeper_scale) & 3) == 0,
                "gemm_i4: activation scale pointers must be 4-byte aligned");
@@ -445,6 +457,7 @@ int gemm_common(const void* a, const void* b, const void* a_scale, const void* b
   args.d = o4 ? nullptr : (__half*)d; args.d4 = o4 ? (uint8_t*)d : nullptr; args.d_scale = (__half2*)d_scale;
   args.M = (int)M; args.N = (int)N; args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M); args.trace = g_trace;
   args.a4 = (const uint8_t*)a; args.a8 = (const int8_t*)a_keeper; args.ldb_scale = (int)N;
+  if (ar != nullptr) args.ar = *ar;
   return o4 ? gemm_dispatch<true>(op, args, flags, (cudaStream_t)stream) : gemm_dispatch<false>(op, args, flags, (cudaStream_t)stream);
 }
 
@@ -484,11 +497,11 @@ int atom_rmsnorm_fp16_i4(const void* hidden, const void* weight, float eps, cons
   if (rc) return rc;
   ATOM_REQUIRE(hidden && weight && reorder_index && aligned16(hidden) && aligned16(weight), "rmsnorm_fp16_i4: null or misaligned input");
   ATOM_REQUIRE(hidden_dim <= 32768, "rmsnorm_fp16_i4: hidden_dim=%d > 32768 unsupported", hidden_dim);
-  if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel, 32768 * 4 + 512, "rmsnorm_fp16_i4"))) return rc;   // row + weight (fp16) + reduction scratch
-  return launch_k("rmsnorm_fp16_i4", atom::rmsnorm_quant_kernel, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 4 + 512,
+  if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel<false>, 32768 * 4 + 512, "rmsnorm_fp16_i4"))) return rc;   // row + weight (fp16) + reduction scratch
+  return launch_k("rmsnorm_fp16_i4", atom::rmsnorm_quant_kernel<false>, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 4 + 512,
                   (cudaStream_t)stream, (const __half*)hidden, (const __half*)nullptr, (__half*)nullptr, (const __half*)weight, eps,
                   (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales,
-                  (__half*)norm_scales, atom::scale_size(seq_len));
+                  (__half*)norm_scales, atom::scale_size(seq_len), atom::ArArgs{});
 }
 
 int atom_add_rmsnorm_fp16_i4(const void* hidden, const void* residual, void* sum_out, const void* weight, float eps,
@@ -499,11 +512,30 @@ int atom_add_rmsnorm_fp16_i4(const void* hidden, const void* residual, void* sum
   ATOM_REQUIRE(hidden && residual && sum_out && weight && reorder_index && aligned16(hidden) && aligned16(residual) && aligned16(sum_out) &&
                aligned16(weight), "add_rmsnorm_fp16_i4: null or misaligned input");
   ATOM_REQUIRE(hidden_dim <= 32768, "add_rmsnorm_fp16_i4: hidden_dim=%d > 32768 unsupported", hidden_dim);
-  if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel, 32768 * 4 + 512, "add_rmsnorm_fp16_i4"))) return rc;
-  return launch_k("add_rmsnorm_fp16_i4", atom::rmsnorm_quant_kernel, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 4 + 512,
+  if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel<false>, 32768 * 4 + 512, "add_rmsnorm_fp16_i4"))) return rc;
+  return launch_k("add_rmsnorm_fp16_i4", atom::rmsnorm_quant_kernel<false>, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 4 + 512,
                   (cudaStream_t)stream, (const __half*)hidden, (const __half*)residual, (__half*)sum_out, (const __half*)weight, eps,
                   (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales,
-                  (__half*)norm_scales, atom::scale_size(seq_len));
+                  (__half*)norm_scales, atom::scale_size(seq_len), atom::ArArgs{});
+}
+
+// reduce half of the fused all-reduce: `hidden` is the sum over the ranks of what atom_gemm_i4_o16_push stored in the receive buffers
+int atom_reduce_add_rmsnorm_fp16_i4(const void* peer_buffers, void* state, int64_t slot_elems, int rank, int world, const void* residual,
+                                    void* sum_out, const void* weight, float eps, const void* reorder_index, int seq_len, int hidden_dim,
+                                    void* o_outliers, void* o_norms, void* outlier_scales, void* norm_scales, void* stream) {
+  int rc = quant_check("reduce_add_rmsnorm_fp16_i4", seq_len, hidden_dim, o_outliers, o_norms, outlier_scales, norm_scales);
+  if (rc) return rc;
+  ATOM_REQUIRE(peer_buffers && state && residual && sum_out && weight && reorder_index && aligned16(residual) && aligned16(sum_out) &&
+               aligned16(weight), "reduce_add_rmsnorm_fp16_i4: null or misaligned input");
+  ATOM_REQUIRE(hidden_dim <= 32768 && hidden_dim % 1024 == 0, "reduce_add_rmsnorm_fp16_i4: hidden_dim=%d must be a multiple of 1024, at most 32768", hidden_dim);
+  ATOM_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world && slot_elems % 8 == 0 && (int64_t)seq_len * hidden_dim <= slot_elems,
+               "reduce_add_rmsnorm_fp16_i4: rank=%d world=%d, %d x %d must fit a slot of %lld elements", rank, world, seq_len, hidden_dim, (long long)slot_elems);
+  if ((rc = ensure_dynamic_smem(atom::rmsnorm_quant_kernel<true>, 32768 * 4 + 512, "reduce_add_rmsnorm_fp16_i4"))) return rc;
+  atom::ArArgs ar{(void* const*)peer_buffers, (uint32_t*)state, (long long)slot_elems, rank, world};
+  return launch_k("reduce_add_rmsnorm_fp16_i4", atom::rmsnorm_quant_kernel<true>, dim3(seq_len), dim3(atom::QUANT_THREADS), (size_t)hidden_dim * 4 + 512,
+                  (cudaStream_t)stream, (const __half*)nullptr, (const __half*)residual, (__half*)sum_out, (const __half*)weight, eps,
+                  (const int16_t*)reorder_index, seq_len, hidden_dim, (int8_t*)o_outliers, (uint8_t*)o_norms, (__half*)outlier_scales,
+                  (__half*)norm_scales, atom::scale_size(seq_len), ar);
 }
 
 int atom_activate_fp16_i4(const void* a, const void* b, int seq_len, int hidden_dim, void* o_outliers, void* o_norms,
@@ -522,6 +554,16 @@ int atom_gemm_i4_o16(const void* a, const void* b, const void* a_scale, const vo
                      int64_t N, int64_t K, uint32_t flags, void* stream) {
   return gemm_common(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, d, nullptr, M, N, K,
                      flags, stream, false);
+}
+
+// push half of the fused all-reduce (row-parallel projection): D is stored into every rank's receive buffer
+int atom_gemm_i4_o16_push(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
+                          const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, const void* peer_buffers,
+                          void* state, int64_t slot_elems, int rank, int world, int64_t M, int64_t N, int64_t K, uint32_t flags,
+                          void* stream) {
+  atom::ArArgs ar{(void* const*)peer_buffers, (uint32_t*)state, (long long)slot_elems, rank, world};
+  return gemm_common(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, nullptr, nullptr, M, N, K, flags,
+                     stream, false, &ar);
 }
 
 int atom_gemm_i4_qkv(const void* a, const void* b_qkv, const void* a_scale, const void* b_scale_qkv, const void* a_keeper,
@@ -627,8 +669,8 @@ int atom_allreduce_push_f16(const void* in, void* out, const void* peer_buffers,
   ATOM_REQUIRE(numel > 0 && numel % 8 == 0 && numel <= slot_elems && slot_elems % 8 == 0,
                "allreduce_push_f16: numel=%lld must be a positive multiple of 8 and fit a slot of %lld elements", (long long)numel, (long long)slot_elems);
   ATOM_REQUIRE(aligned16(in) && aligned16(out), "allreduce_push_f16: in / out must be 16-byte aligned");
-  atom::allreduce_push_kernel<<<atom::AR_CTAS, atom::AR_THREADS, 0, (cudaStream_t)stream>>>(
-      (const uint4*)in, (uint4*)out, (uint4* const*)peer_buffers, (uint32_t*)state, numel / 8, slot_elems / 8, rank, world);
+  atom::ArArgs ar{(void* const*)peer_buffers, (uint32_t*)state, (long long)slot_elems, rank, world};
+  atom::allreduce_push_kernel<<<atom::AR_CTAS, atom::AR_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, ar, numel / 8);
   return check_launch("allreduce_push_f16");
 }
 

@@ -11,98 +11,45 @@
 //   2. it resets ITS OWN buffer [(e + 2) % 3] -- the one read in the previous call -- to the sentinel for a later call;
 //   3. it polls the `world` slots of its slice in LOCAL memory until no 16-byte chunk holds a sentinel half (a torn write
 //      just keeps it polling), sums them in rank order in FP32 (identical on every rank) and writes the FP16 result.
-// Three buffers rotate on a device-side epoch counter, so the kernel is CUDA-graph capturable and needs no barrier: a peer
+// Three buffers rotate on a device-side call counter (published by the last CTA of the consuming kernel), so the kernel is CUDA-graph capturable and needs no barrier: a peer
 // can write buffer e % 3 again only in call e + 3, which it reaches after my push of call e + 2, i.e. after I finished
 // call e; and buffer (e + 2) % 3 is not written by anybody before call e + 2, which every peer reaches only after my push
 // of call e + 1, i.e. after the reset of call e completed (kernel boundary).
 // An earlier revision (fence + one flag per peer + acquire spin) measured 24.6 us for 512 KiB over 8 GPUs against 31.6 us
 // for ncclAllReduce (profiles/r02_tp_check_n8.jsonl).
+// The two halves also exist fused into their neighbours (tp.py): the row-parallel decode GEMM pushes from its epilogue
+// (gemm_i4_skinny_sm100.cuh, GemmArgs::ar) and rmsnorm_quant_kernel reduces while it loads its row (quant_kernels.cuh);
+// the shared pieces live in ptx_sm100.cuh (ArArgs, ar_*).
 #pragma once
 #include "ptx_sm100.cuh"
 
 namespace atom {
 
 constexpr int AR_CTAS = 64, AR_THREADS = 256;
-constexpr int AR_STATE_WORDS = AR_CTAS + 4;     // epoch per CTA, then the chunk count last written into each of the 3 buffers
 
-__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_volatile_v4(void* p, const uint4 v) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// FP16 -0.0 (0x8000) in either half of w
-__device__ __forceinline__ bool has_sentinel(uint32_t w) { return (w & 0xFFFFu) == 0x8000u || (w >> 16) == 0x8000u; }
-__device__ __forceinline__ uint32_t strip_sentinel(uint32_t w) {
-  if ((w & 0xFFFFu) == 0x8000u) w &= 0xFFFF0000u;
-  if ((w >> 16) == 0x8000u) w &= 0x0000FFFFu;
-  return w;
-}
-
-// in, out: f16 [numel] local; bufs[r]: rank r's receive buffer, f16 [3][world][slot_elems], filled with 0x8000 once;
-// state: u32 [AR_STATE_WORDS] local, zeroed once.  numel % 8 == 0, numel <= slot_elems.
+// in, out: f16 [numel] local.  numel % 8 == 0, numel <= ar.slot.
 __global__ void __launch_bounds__(AR_THREADS)
-allreduce_push_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint4* const* __restrict__ bufs, uint32_t* __restrict__ state,
-                      long long nchunks, long long slot_chunks, int rank, int world) {
-  __shared__ uint32_t e_s, last_s;
+allreduce_push_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, ArArgs ar, long long nchunks) {
   const int tid = threadIdx.x, bid = blockIdx.x;
-  if (tid == 0) { e_s = state[bid] + 1; last_s = state[AR_CTAS + (e_s + 2) % 3]; }
-  __syncthreads();
-  const uint32_t e = e_s, cur = e % 3, clr = (e + 2) % 3;
+  const uint32_t e = ar_ld_state(ar.state) + 1, cur = e % 3;
+  const long long slot_chunks = ar.slot / 8;
   const long long per = (nchunks + gridDim.x - 1) / gridDim.x;
   const long long lo = min((long long)bid * per, nchunks), hi = min(lo + per, nchunks);
   // 1. push my slice into slot [cur][rank] of every rank (my own included: the reduction below is then uniform)
   for (long long i = lo + tid; i < hi; i += AR_THREADS) {
     uint4 v = in[i];
-    v.x = strip_sentinel(v.x); v.y = strip_sentinel(v.y); v.z = strip_sentinel(v.z); v.w = strip_sentinel(v.w);
-    for (int r = 0; r < world; ++r)      // destinations staggered by rank: no two ranks start on the same peer
-      st_volatile_v4(bufs[(rank + r) % world] + ((long long)cur * world + rank) * slot_chunks + i, v);
+    v.x = ar_strip_sentinel(v.x); v.y = ar_strip_sentinel(v.y); v.z = ar_strip_sentinel(v.z); v.w = ar_strip_sentinel(v.w);
+    for (int r = 0; r < ar.world; ++r)      // destinations staggered by rank: no two ranks start on the same peer
+      ar_st_v4(reinterpret_cast<uint4*>(ar.bufs[(ar.rank + r) % ar.world]) + ((long long)cur * ar.world + ar.rank) * slot_chunks + i, v);
   }
-  // 2. reset the buffer of the previous call: whatever was written into it (possibly a longer message than this one)
-  {
-    const long long cchunks = max((long long)last_s, 0ll);
-    const long long cper = (cchunks + gridDim.x - 1) / gridDim.x;
-    const long long clo = min((long long)bid * cper, cchunks), chi = min(clo + cper, cchunks);
-    const uint4 sv = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
-    uint4* base = bufs[rank] + (long long)clr * world * slot_chunks;
-    for (int r = 0; r < world; ++r)
-      for (long long i = clo + tid; i < chi; i += AR_THREADS) base[(long long)r * slot_chunks + i] = sv;
-  }
+  // 2. reset the buffer of the previous call
+  ar_reset_previous(ar, e, bid, gridDim.x, tid, AR_THREADS);
   // 3. poll + reduce in rank order from local memory
-  const uint4* local = bufs[rank] + (long long)cur * world * slot_chunks;
+  const uint4* local = reinterpret_cast<const uint4*>(ar.bufs[ar.rank]) + (long long)cur * ar.world * slot_chunks;
   unsigned long long t0 = 0;
-  for (long long i = lo + tid; i < hi; i += AR_THREADS) {
-    float acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int r = 0; r < world; ++r) {
-      uint4 v = ld_volatile_v4(local + (long long)r * slot_chunks + i);     // written remotely: do not trust L1
-      // bounded: a peer that never arrives (crashed rank, mismatched call sequence) traps after ~4 s instead of hanging the GPU
-      for (uint32_t spins = 0; has_sentinel(v.x) || has_sentinel(v.y) || has_sentinel(v.z) || has_sentinel(v.w); ++spins) {
-        if ((spins & 0x3FFu) == 0x3FFu) {
-          unsigned long long now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > 4000000000ull) asm volatile("trap;");
-        }
-        v = ld_volatile_v4(local + (long long)r * slot_chunks + i);
-      }
-      const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
-    }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
-    out[i] = o;
-  }
-  if (tid == 0) {
-    state[bid] = e;
-    if (bid == 0) state[AR_CTAS + cur] = (uint32_t)nchunks;     // read again (as `last`) by call e + 1, a later kernel
-  }
+  for (long long i = lo + tid; i < hi; i += AR_THREADS) out[i] = ar_reduce_chunk(local, slot_chunks, i, ar.world, t0);
+  __syncthreads();
+  if (tid == 0) ar_complete(ar, e, nchunks, gridDim.x);
 }
 
 }  // namespace atom

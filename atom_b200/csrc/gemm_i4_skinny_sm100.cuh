@@ -37,7 +37,8 @@ namespace atom {
 // channels, each streaming the whole K range); rank 1 hands its FP32 sums to rank 0 through DSMEM, rank 0 applies
 // SiLU(gate) * up and the dynamic per-(token, 128-channel group) quantisation of activate_fp16_i4 and writes the INT4 / INT8
 // operands of the down projection directly: no FP16 round trip through HBM, no activation kernel.
-enum { EPI_O16 = 0, EPI_O4 = 1, EPI_QKV = 2, EPI_GATEUP = 3 };
+// EPI_PUSH: EPI_O16 whose result goes to every rank's all-reduce receive buffer (GemmArgs::ar; tp.py row-parallel projections).
+enum { EPI_O16 = 0, EPI_O4 = 1, EPI_QKV = 2, EPI_GATEUP = 3, EPI_PUSH = 4 };
 
 template <int BN, int kSplit, int kEpi>
 struct SkinnyCfg {
@@ -67,14 +68,14 @@ struct SkinnyCfg {
   static constexpr int RED_BYTES = BM * CPR * 4;                       // one source rank's partial for this rank's columns
   static constexpr int OFF_RED = OFF_SA + SC * BN * 2;
   static constexpr int OFF_XCH = OFF_RED + (kSplit > 1 ? (kSplit - 1) * RED_BYTES : 0);   // o4: per-warp |v| min/max
-  static constexpr int OFF_BAR = OFF_XCH + (kEpi != EPI_O16 ? 8 * BN * 4 : 0);     // gate/up uses the first 4 * BN floats
+  static constexpr int OFF_BAR = OFF_XCH + (kEpi != EPI_O16 && kEpi != EPI_PUSH ? 8 * BN * 4 : 0);     // gate/up uses the first 4 * BN floats
   static constexpr int NUM_BARS = 2 * PACK + 2 * A_PAIRS + 4 + ACC_PAIRS + 3;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
   static constexpr int CTAS_PER_SM = ONE_PER_SM ? 1 : 2;
   static_assert(BN == 16 || BN == 32 || BN == 64, "token tile");
   static_assert(BN % kSplit == 0 && CPR >= 2, "every split-K rank owns at least 2 token columns (one 8-byte st.async)");
-  static_assert(kEpi == EPI_O16 || (kEpi == EPI_GATEUP && kSplit == 2) || kSplit == 1, "the quantising epilogues work on un-split FP32 sums");
+  static_assert(kEpi == EPI_O16 || kEpi == EPI_PUSH || (kEpi == EPI_GATEUP && kSplit == 2) || kSplit == 1, "the quantising epilogues work on un-split FP32 sums");
   static_assert(A_PAIRS * 64 + ACC_PAIRS * 2 * BN <= TMEM_COLS, "tensor memory budget");
   static_assert(A_PAIRS >= ACC_PAIRS, "mma_done is indexed by operand slot");
   static_assert(ONE_PER_SM ? SMEM_BYTES <= 227 * 1024 : SMEM_BYTES <= 113 * 1024, "shared memory budget (two CTAs per SM)");
@@ -514,7 +515,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     const int seg = kEpi == EPI_QKV ? (int)blockIdx.x / args.seg_tiles : 0;
     const int tile = kEpi == EPI_QKV ? (int)blockIdx.x % args.seg_tiles : (int)blockIdx.x;
     const int n_out_dim = kEpi == EPI_QKV ? args.seg_tiles * 128 : args.N;       // row length of the output this tile writes
-    if (kEpi == EPI_O16 || (kEpi == EPI_QKV && seg == 0)) {
+    if (kEpi == EPI_O16 || kEpi == EPI_PUSH || (kEpi == EPI_QKV && seg == 0)) {
       // ---------------------------------------------------------- split-K: rank d reduces + stores token columns
       // [d * CPR, (d + 1) * CPR).  Partials travel as st.async messages that also complete transaction bytes on the
       // owner's mbarrier: no cluster barrier, and the owner sums in rank order 0..kSplit-1 (deterministic).
@@ -558,11 +559,40 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       if (warp == 8 && lane == 0) trace_stamp(args, 3);
       const int n = tile * C::BM + row;
       if (n < n_out_dim && n0 + row < args.N) {
+        if constexpr (kEpi == EPI_PUSH) {
+          // fused all-reduce, push half: D goes to slot [call % 3][rank] of EVERY rank's receive buffer (-0.0, the buffers'
+          // "not yet arrived" pattern, travels as +0.0); the following add+RMSNorm kernel polls and sums the slots
+          const uint32_t cur = (ar_ld_state(args.ar.state) + 1) % 3;
+          const size_t base = ((size_t)cur * args.ar.world + args.ar.rank) * (size_t)args.ar.slot + n;
+          uint32_t hp[BN / 2];                 // the FP16 results first: the accumulators are dead before the peer loop
 #pragma unroll
-        for (int c = 0; c < BN; ++c) {
-          const int m = m0 + c;
-          if ((kSplit == 1 || c / C::CPR == (int)krank) && m < args.M)
-            args.d[(size_t)m * n_out_dim + n] = __float2half_rn(acc[c] * kInv);      // a warp writes 64-B runs
+          for (int c = 0; c < BN; c += 2) {
+            unsigned short h0 = __half_as_ushort(__float2half_rn(acc[c] * kInv)), h1 = __half_as_ushort(__float2half_rn(acc[c + 1] * kInv));
+            if (h0 == 0x8000u) h0 = 0;
+            if (h1 == 0x8000u) h1 = 0;
+            hp[c >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          }
+#pragma unroll 1
+          for (int r = 0; r < args.ar.world; ++r) {
+            __half* dst = reinterpret_cast<__half*>(args.ar.bufs[(args.ar.rank + r) % args.ar.world]) + base + (size_t)m0 * n_out_dim;
+#pragma unroll
+            for (int d = 0; d < kSplit; ++d) {
+              if (kSplit == 1 || d == (int)krank) {        // uniform per CTA: this rank's token columns
+#pragma unroll
+                for (int j = 0; j < C::CPR; ++j) {
+                  const int c = d * C::CPR + j;
+                  if (m0 + c < args.M) ar_st_u16(dst + (size_t)c * n_out_dim, (unsigned short)(hp[c >> 1] >> (16 * (c & 1))));
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN; ++c) {
+            const int m = m0 + c;
+            if ((kSplit == 1 || c / C::CPR == (int)krank) && m < args.M)
+              args.d[(size_t)m * n_out_dim + n] = __float2half_rn(acc[c] * kInv);      // a warp writes 64-B runs
+          }
         }
       }
     } else {

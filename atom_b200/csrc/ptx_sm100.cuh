@@ -219,4 +219,91 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
   return v;
 }
 
+// ---------------------------------------------------------------- push all-reduce (comm_kernels.cuh) state shared with
+// the kernels that fuse its two halves: the row-parallel GEMM pushes its partial straight into the peers' receive buffers,
+// the following add+RMSNorm+quantise kernel reduces them (tp.py).  bufs[r]: rank r's receive buffer, f16 [3][world][slot],
+// sentinel-filled (0x8000); state (local u32): [0] completed calls, [1] ticket, [2..4] chunks last written per buffer.
+struct ArArgs {
+  void* const* bufs;
+  uint32_t* state;
+  long long slot;          // elements per (buffer, rank) slot
+  int rank, world;
+};
+constexpr int AR_STATE_WORDS = 8;
+__device__ __forceinline__ uint32_t ar_ld_state(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ar_ld_v4(const void* p) {      // written remotely: never through L1
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ar_st_v4(void* p, const uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void ar_st_u16(void* p, unsigned short v) {
+  asm volatile("st.volatile.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
+}
+// FP16 -0.0 (0x8000) is the "not yet arrived" pattern of the receive buffers
+__device__ __forceinline__ bool ar_has_sentinel(uint32_t w) { return (w & 0xFFFFu) == 0x8000u || (w >> 16) == 0x8000u; }
+__device__ __forceinline__ bool ar_has_sentinel(const uint4& v) {
+  return ar_has_sentinel(v.x) || ar_has_sentinel(v.y) || ar_has_sentinel(v.z) || ar_has_sentinel(v.w);
+}
+__device__ __forceinline__ uint32_t ar_strip_sentinel(uint32_t w) {
+  if ((w & 0xFFFFu) == 0x8000u) w &= 0xFFFF0000u;
+  if ((w >> 16) == 0x8000u) w &= 0x0000FFFFu;
+  return w;
+}
+// one 16-byte chunk of the sum: poll the `world` slots in local memory until the payload is there, add in rank order (FP32)
+__device__ __forceinline__ uint4 ar_reduce_chunk(const uint4* local_cur, long long slot_chunks, long long i, int world, unsigned long long& t0) {
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const uint4* src = local_cur + (long long)r * slot_chunks + i;
+    uint4 v = ar_ld_v4(src);
+    // bounded: a peer that never arrives (crashed rank, mismatched call sequence) traps after ~4 s instead of hanging the GPU
+    for (uint32_t spins = 0; ar_has_sentinel(v); ++spins) {
+      if ((spins & 0x3FFu) == 0x3FFu) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) asm volatile("trap;");
+      }
+      v = ar_ld_v4(src);
+    }
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+  }
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+  return o;
+}
+// this CTA's share of resetting the buffer of the previous call (whatever extent was written into it) to the sentinel
+__device__ __forceinline__ void ar_reset_previous(const ArArgs& ar, uint32_t e, int cta, int nctas, int tid, int nthreads) {
+  const uint32_t clr = (e + 2) % 3;
+  const long long cchunks = (long long)ar_ld_state(ar.state + 2 + clr), slot_chunks = ar.slot / 8;
+  const long long cper = (cchunks + nctas - 1) / nctas;
+  const long long clo = min((long long)cta * cper, cchunks), chi = min(clo + cper, cchunks);
+  const uint4 sv = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+  uint4* base = reinterpret_cast<uint4*>(ar.bufs[ar.rank]) + (long long)clr * ar.world * slot_chunks;
+  for (int r = 0; r < ar.world; ++r)
+    for (long long i = clo + tid; i < chi; i += nthreads) base[(long long)r * slot_chunks + i] = sv;
+}
+// end of a consuming kernel: the last CTA to get here publishes the call (all CTAs read state[0] when they started)
+__device__ __forceinline__ void ar_complete(const ArArgs& ar, uint32_t e, long long nchunks, int nctas) {
+  __threadfence();
+  if (atomicAdd(ar.state + 1, 1u) == (uint32_t)nctas - 1) {
+    ar.state[2 + e % 3] = (uint32_t)nchunks;
+    ar.state[1] = 0;
+    __threadfence();
+    ar.state[0] = e;
+  }
+}
+
 }  // namespace atom

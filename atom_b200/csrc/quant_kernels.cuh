@@ -80,13 +80,21 @@ reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ i
 // so the chain is kept short: 2 groups per warp at hidden 4096 instead of 8).
 // With `residual` != nullptr the row is x + residual (one FP16 RN add per element, exactly what `residual + hidden_states`
 // does in the reference's decoder layer, llama.py:266-292); the sum is also written to `sum_out` (the next residual).
+template <bool kReduce>   // kReduce: x is the all-reduced sum, formed on the fly from the push all-reduce's receive buffers
 __global__ void __launch_bounds__(QUANT_THREADS)
 rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ residual, __half* __restrict__ sum_out,
                      const __half* __restrict__ w, float eps, const int16_t* __restrict__ idx,
                      int seq_len, int hidden, int8_t* __restrict__ s8out, uint8_t* __restrict__ s4out,
-                     __half* __restrict__ s8scale, __half* __restrict__ s4scale, int scale_ldm, int pdl) {
+                     __half* __restrict__ s8scale, __half* __restrict__ s4scale, int scale_ldm, ArArgs ar, int pdl) {
   extern __shared__ __align__(16) uint8_t smem_q[];
   if (pdl) { griddep_launch_dependents(); griddep_wait(); }
+  // kReduce: x is the sum over the ranks of the row-parallel projection's partials, which the GEMM pushed into the
+  // receive buffers (reduce half of the push all-reduce, comm_kernels.cuh): each 16-byte chunk is polled until its payload has
+  // arrived and summed in rank order in FP32, rounded to FP16 -- the value the stand-alone all-reduce would have delivered
+  const uint32_t ar_e = kReduce ? ar_ld_state(ar.state) + 1 : 0;
+  const uint4* ar_local = kReduce
+      ? reinterpret_cast<const uint4*>(ar.bufs[ar.rank]) + (long long)(ar_e % 3) * ar.world * (ar.slot / 8) : nullptr;
+  unsigned long long ar_t0 = 0;
   __half* xs = reinterpret_cast<__half*>(smem_q);
   __half* ws = xs + hidden;                             // norm weight staged too: the gather then never touches global
   float* red = reinterpret_cast<float*>(smem_q + (size_t)hidden * 4);
@@ -102,7 +110,8 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ re
       reinterpret_cast<uint4*>(ws)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(w) + i);
   } else if ((ept & 7) == 0) {
     for (int i = 0; i < ept; i += 8) {
-      uint4 u = *reinterpret_cast<const uint4*>(xr + tid * ept + i);
+      uint4 u = kReduce ? ar_reduce_chunk(ar_local, ar.slot / 8, ((long long)row * hidden + tid * ept + i) / 8, ar.world, ar_t0)
+                                    : *reinterpret_cast<const uint4*>(xr + tid * ept + i);
       if (residual != nullptr) {
         const uint4 rr = *reinterpret_cast<const uint4*>(residual + (size_t)row * hidden + tid * ept + i);
         __half2* hu = reinterpret_cast<__half2*>(&u);
@@ -156,6 +165,11 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ re
       v[i] = __half2float(__float2half_rn(y));
     }
     quant_group_store(v, lane, row, g, ng, scale_ldm, s8out, s4out, s8scale, s4scale, hidden);
+  }
+  if (kReduce) {     // housekeeping of the fused all-reduce, off the critical path
+    ar_reset_previous(ar, ar_e, blockIdx.x, gridDim.x, tid, QUANT_THREADS);
+    __syncthreads();
+    if (tid == 0) ar_complete(ar, ar_e, (long long)seq_len * hidden / 8, gridDim.x);
   }
 }
 

@@ -254,7 +254,10 @@ class LlamaRMSNormInt4(nn.Module):
         return ops.rmsnorm_fp16_i4(hidden_states, self.weight, self.reorder_index, self.variance_epsilon)
 
     def forward_add(self, hidden_states, residual):
-        """(residual + hidden_states, norm+quantise of that sum) in one launch."""
+        """(residual + hidden_states, norm+quantise of that sum) in one launch.  hidden_states may be an ops.PendingAllReduce
+        (tensor parallelism): the all-reduce is then formed inside the same launch."""
+        if isinstance(hidden_states, ops.PendingAllReduce):
+            return ops.reduce_add_rmsnorm_fp16_i4(hidden_states, residual, self.weight, self.reorder_index, self.variance_epsilon)
         return ops.add_rmsnorm_fp16_i4(hidden_states, residual, self.weight, self.reorder_index, self.variance_epsilon)
 
 

@@ -141,6 +141,62 @@ def dense_layer_gemm_i4_fp16(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keepe
     return d
 
 
+class ArHandle:
+    """What the fused all-reduce entry points need of a comm.PushAllReduce: the device table of every rank's receive buffer, the
+    local call-counter block, the slot size, and this rank's place in the group."""
+    __slots__ = ("peer_ptrs", "state", "slot", "rank", "world")
+
+    def __init__(self, peer_ptrs, state, slot, rank, world):
+        self.peer_ptrs, self.state, self.slot, self.rank, self.world = int(peer_ptrs), state, int(slot), int(rank), int(world)
+
+
+class PendingAllReduce:
+    """Result of dense_layer_gemm_i4_fp16_push: the partial products sit in the receive buffers of all ranks; only
+    reduce_add_rmsnorm_fp16_i4 (the very next consumer) can turn them into the all-reduced tensor."""
+    __slots__ = ("ar", "shape", "device")
+
+    def __init__(self, ar, shape, device):
+        self.ar, self.shape, self.device = ar, tuple(shape), device
+
+
+def dense_layer_gemm_i4_fp16_push(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, ar, flags=GEMM_AUTO):
+    """EXTENSION (tensor parallelism, decode batches M <= 64): dense_layer_gemm_i4_fp16 of a row-parallel shard whose epilogue pushes
+    the FP16 partial into every rank's all-reduce receive buffer (csrc/comm_kernels.cuh).  Returns a PendingAllReduce."""
+    _req_width("dense_layer_gemm_i4_fp16_push", a_1=a, b_1=b, f16_a_scale_2=a_scale, f16_b_scale_2=b_scale, a_keeper_1=a_keeper,
+               b_keeper_1=b_keeper, f16_a_keeper_scale_2=a_keeper_scale, f16_b_keeper_scale_2=b_keeper_scale)
+    _req_cuda(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale)
+    m, n = a.size(0), b.size(0)
+    k = a.size(1) * 2 + a_keeper.size(1)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().atom_gemm_i4_o16_push(a.data_ptr(), b.data_ptr(), a_scale.data_ptr(), b_scale.data_ptr(),
+                                                    a_keeper.data_ptr(), b_keeper.data_ptr(), a_keeper_scale.data_ptr(),
+                                                    b_keeper_scale.data_ptr(), ar.peer_ptrs, ar.state.data_ptr(), ar.slot, ar.rank,
+                                                    ar.world, m, n, k, flags, _stream(a)), "dense_layer_gemm_i4_fp16_push")
+    return PendingAllReduce(ar, (m, n), a.device)
+
+
+def reduce_add_rmsnorm_fp16_i4(pending, residual, weight, reorder_index, eps):
+    """EXTENSION: add_rmsnorm_fp16_i4 whose `hidden_states` is the all-reduce of a PendingAllReduce, formed while the row is loaded.
+    Returns (sum, 4-tuple), bit-identical to all-reducing first (rank-order FP32 sum, FP16 result) and calling add_rmsnorm_fp16_i4."""
+    if isinstance(weight, torch.Tensor) and weight.dtype != torch.float16:
+        weight = weight.to(torch.float16)
+    _req_width("reduce_add_rmsnorm_fp16_i4", f16_residual_2=residual, f16_weight_2=weight, reorder_index_2=reorder_index)
+    _req_cuda(residual, weight, reorder_index)
+    if tuple(residual.shape) != pending.shape:
+        raise RuntimeError("reduce_add_rmsnorm_fp16_i4: residual must have the shape of the pending all-reduce")
+    bs, hidden_dim = residual.shape
+    out = _quant_outputs(bs, hidden_dim, residual.device)
+    s = torch.empty_like(residual)
+    ar = pending.ar
+    with torch.cuda.device(residual.device):
+        _lib.check(_lib.lib().atom_reduce_add_rmsnorm_fp16_i4(ar.peer_ptrs, ar.state.data_ptr(), ar.slot, ar.rank, ar.world,
+                                                              residual.data_ptr(), s.data_ptr(), weight.data_ptr(), float(eps),
+                                                              reorder_index.data_ptr(), bs, hidden_dim, out[0].data_ptr(),
+                                                              out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                                              _stream(residual)), "reduce_add_rmsnorm_fp16_i4")
+    return s, out
+
+
 def dense_layer_gemm_i4_o4(a, b, a_scale, b_scale, a_keeper, b_keeper, a_keeper_scale, b_keeper_scale, flags=GEMM_AUTO):
     """ops/__init__.py:171-176"""
     _req_width("dense_layer_gemm_i4_o4", a_1=a, b_1=b, f16_a_scale_2=a_scale, f16_b_scale_2=b_scale, a_keeper_1=a_keeper,

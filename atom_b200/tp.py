@@ -70,6 +70,18 @@ class RowParallelLinearInt4(nn.Module):
         self.gemm_fn = gemm_fn
         self.allreduce = allreduce       # comm.PushAllReduce / NcclAllReduce; None = plain dist.all_reduce
 
+    def can_push(self, batch):
+        """Fused all-reduce (GEMM epilogue pushes, the following add+RMSNorm reduces): push kernel, decode batch, wide rows."""
+        return (self.world > 1 and self.gemm_fn is None and getattr(self.allreduce, "handle", None) is not None and batch <= 64
+                and self.local.out_features % 1024 == 0 and batch * self.local.out_features <= self.allreduce.slot)
+
+    def forward_push(self, local_tuple):
+        """The GEMM only; its partial goes straight into every rank's receive buffer.  The caller must hand the returned
+        ops.PendingAllReduce to LlamaRMSNormInt4.forward_add before anything else uses this all-reduce object."""
+        outlier, norms, outlier_scales, norm_scales = local_tuple
+        return ops.dense_layer_gemm_i4_fp16_push(norms, self.local.weight_int4, norm_scales, self.local.scale_int4, outlier,
+                                                 self.local.weight_int8, outlier_scales, self.local.scale_int8, self.allreduce.handle)
+
     def forward(self, local_tuple):
         outlier, norms, outlier_scales, norm_scales = local_tuple
         f = self.gemm_fn or ops.dense_layer_gemm_i4_fp16
@@ -127,8 +139,18 @@ class TPLlamaDecoderLayer(nn.Module):
         return self
 
     def forward(self, hidden_states, decode_kv):
+        hidden_states, pending = self.forward_chain(hidden_states, None, decode_kv, last=True)
+        return hidden_states
+
+    def forward_chain(self, hidden_states, pending, decode_kv, last=False):
+        """One decode step.  `pending`: the previous layer's down projection whose all-reduce has not been formed yet (it is, together
+        with the residual add, inside this layer's input norm launch).  Returns (hidden_states, pending'): with last=False and a
+        push-capable all-reduce the down projection of this layer is returned pending, otherwise it is reduced and added here."""
         b = hidden_states.shape[0]
-        x = self.input_layernorm(hidden_states)
+        if pending is not None:
+            hidden_states, x = self.input_layernorm.forward_add(pending, hidden_states)
+        else:
+            x = self.input_layernorm(hidden_states)
         fused = getattr(self, "_qkv", None) is not None and b <= 64
         if fused:
             w4, s4, w8, s8 = self._qkv
@@ -141,11 +163,14 @@ class TPLlamaDecoderLayer(nn.Module):
         ops.append_kv_i4(decode_kv, k.view(b, self.local_heads, 64), v.view(b, self.local_heads, 64),
                          ks.view(b, self.local_heads, 2), vs.view(b, self.local_heads, 2), self.layer_idx)
         attn = ops.batch_decode_i4(q, decode_kv, self.layer_idx).view(b, self.local_heads * 128)
-        o = self.o_proj(ops.reorder_fp16_i4(attn, self.attn_reorder_index))                                  # all-reduce #1
-        hidden_states, x = self.post_attention_layernorm.forward_add(o, hidden_states)                        # residual add folded into the norm
+        o_in = ops.reorder_fp16_i4(attn, self.attn_reorder_index)
+        o = self.o_proj.forward_push(o_in) if self.o_proj.can_push(b) else self.o_proj(o_in)                  # all-reduce #1
+        hidden_states, x = self.post_attention_layernorm.forward_add(o, hidden_states)                        # residual add (+ reduce) folded into the norm
         if fused:
             w4, s4, w8, s8 = self._gu
             act = ops.dense_layer_gemm_i4_gateup_act(x[1], w4, x[3], s4, x[0], w8, x[2], s8)
         else:
             act = ops.activate_fp16_i4(self.gate_proj(x), self.up_proj(x))
-        return hidden_states + self.down_proj(act)                                                           # all-reduce #2
+        if not last and self.down_proj.can_push(b):
+            return hidden_states, self.down_proj.forward_push(act)                                           # all-reduce #2, formed by the next layer's norm
+        return hidden_states + self.down_proj(act), None                                                     # all-reduce #2

@@ -190,9 +190,11 @@ def tp_decode_layer(rank, world, dev, hidden=8192, inter=22016, heads=64, batch=
     x = torch.randn(batch, hidden, device=dev, dtype=torch.float16)
 
     def step():
-        y = x
-        for l, kv in zip(mods, kvs):
-            y = l(y, kv)
+        # consecutive layers hand their down projection over un-reduced: its all-reduce (like o_proj's) is formed inside the next
+        # add+RMSNorm launch from what the GEMM epilogues pushed into the peers' receive buffers (push all-reduce only)
+        y, pend = x, None
+        for i, (l, kv) in enumerate(zip(mods, kvs)):
+            y, pend = l.forward_chain(y, pend, kv, last=(i == len(mods) - 1))
         return y
 
     st = torch.cuda.Stream(dev)
@@ -226,6 +228,7 @@ def tp_decode_layer(rank, world, dev, hidden=8192, inter=22016, heads=64, batch=
            "tp": world, "batch": batch, "kv_len": kvlen, "us_per_layer": round(us, 1),
            "value": round(batch / (us * layers * 1e-6), 1), "unit": "tokens/s", "scaling": "strong",
            "allreduces_per_layer": 2 if world > 1 else 0, "allreduce": allreduce.name if allreduce is not None else None,
+           "allreduce_fused_into_gemm_and_rmsnorm": bool(world > 1 and mods[0].o_proj.can_push(batch)),
            "allreduce_bytes": batch * hidden * 2 if world > 1 else 0,
            "launch": f"one CUDA graph per step over {copies} chained layer copies ({(w_bytes + kv_bytes) * copies / 1e6:.0f} MB of weights + KV per rank > L2), "
                      "collectives captured inside, device time, max over ranks",

@@ -159,6 +159,24 @@ ATOM_API int atom_allreduce_push_f16(const void* in, void* out, const void* peer
                             int64_t slot_elems, int rank, int world, void* stream);
 ATOM_API int atom_allreduce_state_words(void);
 
+/* The same all-reduce with its two halves fused into the kernels around it (decode batches, M <= 64):
+ *   atom_gemm_i4_o16_push            the row-parallel projection (o_proj / down_proj shard): atom_gemm_i4_o16 whose epilogue stores D
+ *                                    into slot [call % 3][rank] of EVERY rank's receive buffer instead of a local tensor;
+ *   atom_reduce_add_rmsnorm_fp16_i4  atom_add_rmsnorm_fp16_i4 whose `hidden` input is the sum over the ranks of those slots: each
+ *                                    16-byte chunk is polled until its payload has arrived, summed in rank order in FP32 and rounded
+ *                                    to FP16 (bit-identical to what atom_allreduce_push_f16 would have delivered), then added to the
+ *                                    residual, normalised and quantised as usual.  hidden_dim % 1024 == 0.
+ * The pair must be called in this order with the same (peer_buffers, state) and M x N = seq_len x hidden_dim; pairs and stand-alone
+ * atom_allreduce_push_f16 calls on the same buffers may be mixed freely (one call counter). */
+ATOM_API int atom_gemm_i4_o16_push(const void* a, const void* b, const void* a_scale, const void* b_scale, const void* a_keeper,
+                          const void* b_keeper, const void* a_keeper_scale, const void* b_keeper_scale, const void* peer_buffers,
+                          void* state, int64_t slot_elems, int rank, int world, int64_t M, int64_t N, int64_t K, uint32_t flags,
+                          void* stream);
+ATOM_API int atom_reduce_add_rmsnorm_fp16_i4(const void* peer_buffers, void* state, int64_t slot_elems, int rank, int world,
+                                    const void* residual, void* sum_out, const void* weight, float eps, const void* reorder_index,
+                                    int seq_len, int hidden_dim, void* o_outliers, void* o_norms, void* outlier_scales,
+                                    void* norm_scales, void* stream);
+
 /* replaces append_kv_i4 (punica_ops.cc:166-209 -> FlashInferAppendKvKernel_i4<128>, flashinfer_impl.cuh:73-96)
  *   k,v u8 [B,H,64]  k_param,v_param f16 [B,H,2] */
 ATOM_API int atom_append_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,

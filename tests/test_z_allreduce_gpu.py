@@ -78,3 +78,59 @@ def test_argument_validation():
     y = torch.zeros(12, dtype=torch.float16, device=dev)
     with pytest.raises(RuntimeError):
         _call(y, torch.empty_like(y), st, 1024)      # numel % 8 != 0
+
+
+def test_world1_fused_gemm_push_and_reducing_rmsnorm():
+    """The fused pair (row-parallel GEMM pushes from its epilogue, add+RMSNorm+quantise reduces while it loads) against the unfused
+    sequence GEMM -> add_rmsnorm on one GPU (world == 1: the sum has one term, so everything is bit-identical), over several calls
+    (buffer rotation), interleaved with stand-alone all-reduces on the same buffers, eagerly and from a CUDA graph."""
+    import numpy as np
+    from atom_b200 import ops
+    from oracle import oracle as O
+    dev = torch.device("cuda", 0)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    slot = 64 * 4096
+    st = _setup(slot, dev)
+    h = ops.ArHandle(st[2].data_ptr(), st[1], slot, 0, 1)
+    for it, (m, n, k) in enumerate([(16, 4096, 1024), (32, 4096, 512), (7, 2048, 1024), (64, 1024, 512), (16, 4096, 4096)]):
+        t = [T(x) for x in O.make_gemm_inputs(m, n, k, seed=900 + it)]
+        rng = np.random.default_rng(it)
+        res = T((rng.standard_normal((m, n)) * 2).astype(np.float16))
+        w = T((1 + 0.2 * rng.standard_normal(n)).astype(np.float16))
+        idx = T(rng.permutation(n).astype(np.int16))
+        torch.cuda.synchronize()
+        flags = 1 | 4                                  # no split-K, decode kernel: the association of the reference
+        d = ops.dense_layer_gemm_i4_fp16(*t, flags=flags)
+        s_ref, q_ref = ops.add_rmsnorm_fp16_i4(d, res, w, idx, 1e-5)
+        pend = ops.dense_layer_gemm_i4_fp16_push(*t, h, flags=flags)
+        s, q = ops.reduce_add_rmsnorm_fp16_i4(pend, res, w, idx, 1e-5)
+        torch.cuda.synchronize()
+        assert torch.equal(s, s_ref), f"case {it}: sum differs"
+        for a, b in zip(q[:2], q_ref[:2]):
+            assert torch.equal(a, b), f"case {it}: quantised operand differs"
+        if it % 2 == 1:                                # a stand-alone all-reduce in between: same counter, same buffers
+            x = (torch.randn(4096, device=dev) * 3).half()
+            out = torch.empty_like(x)
+            _call(x, out, st, slot)
+            torch.cuda.synchronize()
+            assert torch.equal(out, x)
+    # split-K path (default dispatch) + graph replay: three fused pairs per replay
+    t = [T(x) for x in O.make_gemm_inputs(16, 4096, 4096, seed=77)]
+    res = torch.zeros(16, 4096, dtype=torch.float16, device=dev)
+    w = torch.ones(4096, dtype=torch.float16, device=dev)
+    idx = torch.arange(4096, dtype=torch.int16, device=dev)
+    torch.cuda.synchronize()
+    d = ops.dense_layer_gemm_i4_fp16(*t)               # auto: split-K, deterministic
+    s_ref, q_ref = ops.add_rmsnorm_fp16_i4(d, res, w, idx, 1e-5)
+    sstream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(sstream):
+        ops.reduce_add_rmsnorm_fp16_i4(ops.dense_layer_gemm_i4_fp16_push(*t, h), res, w, idx, 1e-5)
+        sstream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=sstream):
+            outs = [ops.reduce_add_rmsnorm_fp16_i4(ops.dense_layer_gemm_i4_fp16_push(*t, h), res, w, idx, 1e-5) for _ in range(3)]
+        for rep in range(4):
+            g.replay()
+            sstream.synchronize()
+            for s, q in outs:
+                assert torch.equal(s, s_ref) and torch.equal(q[1], q_ref[1]), f"replay {rep}"

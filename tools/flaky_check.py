@@ -1,7 +1,7 @@
 import os, sys, json
 import numpy as np, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
-from oracle import atom_oracle as O
+from oracle import oracle as O
 from atom_b200 import ops
 def T(a, sync):
     t = torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0")

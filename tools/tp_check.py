@@ -106,24 +106,32 @@ for n in (16 * 4096, 32 * 8192):
                                                    "how": "50 chained calls per CUDA graph, 20 replays, device time, max over ranks"}}), flush=True)
 
 # ---------------------------------------------------------------- 2. TP decoder layer: push vs NCCL
+# two chained layers: with the push all-reduce both all-reduces of layer 0 and the first of layer 1 run FUSED (GEMM epilogue pushes,
+# the following add+RMSNorm reduces); the last one is the stand-alone kernel
 hidden, inter, heads, batch, kvlen, page = 4096, 11008, 32, 16, 300, 16
 cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads, num_hidden_layers=1)
 lh = heads // world
 outs = []
 for ar in (PushAllReduce(batch * hidden, dev), NcclAllReduce()):
-    layer = TPLlamaDecoderLayer(cfg, 0, rank, world, allreduce=ar).to(dev).init_random(5)
-    torch.manual_seed(4242 + rank)
-    pool = KvPoolInt4(1, lh, 128, capacity=batch * ((kvlen + page) // page + 1), block_len=page, device=dev)
-    pool.buf.random_(0, 256); pool.param[..., 0].uniform_(0.01, 0.05); pool.param[..., 1].uniform_(0.0, 0.4)
-    caches = [KvCacheInt4(pool, kvlen) for _ in range(batch)]
-    for c in caches:
-        c.acquire_one()
-    kv = BatchedKvCacheInt4(caches)
+    layers = [TPLlamaDecoderLayer(cfg, 0, rank, world, allreduce=ar).to(dev).init_random(5 + i) for i in range(2)]
+    kvs = []
+    for i in range(2):
+        torch.manual_seed(4242 + rank + 17 * i)
+        pool = KvPoolInt4(1, lh, 128, capacity=batch * ((kvlen + page) // page + 1), block_len=page, device=dev)
+        pool.buf.random_(0, 256); pool.param[..., 0].uniform_(0.01, 0.05); pool.param[..., 1].uniform_(0.0, 0.4)
+        caches = [KvCacheInt4(pool, kvlen) for _ in range(batch)]
+        for c in caches:
+            c.acquire_one()
+        kvs.append(BatchedKvCacheInt4(caches))
     torch.manual_seed(99)
     xin = torch.randn(batch, hidden, device=dev, dtype=torch.float16)
-    out = layer(xin, kv)
-    out = out[0] + out[1] if isinstance(out, tuple) else out
-    outs.append(out.float())
+    y, pend = xin, None
+    for i, (l, kv) in enumerate(zip(layers, kvs)):
+        y, pend = l.forward_chain(y, pend, kv, last=(i == 1))
+    assert pend is None
+    if isinstance(ar, PushAllReduce) and rank == 0:
+        print(json.dumps({"fused_allreduce_in_use": bool(layers[0].o_proj.can_push(batch))}), flush=True)
+    outs.append(y.float())
     torch.cuda.synchronize()
 d = (outs[0] - outs[1]).abs().max().item()
 scale = outs[1].abs().max().item()
