@@ -572,16 +572,22 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
             if (h1 == 0x8000u) h1 = 0;
             hp[c >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
           }
+          // peer loop innermost and not unrolled: one live address at a time (this is tail code, registers are scarce here)
+#pragma unroll
+          for (int d = 0; d < kSplit; ++d) {
+            if (kSplit == 1 || d == (int)krank) {          // uniform per CTA: this rank's token columns
+#pragma unroll
+              for (int j = 0; j < C::CPR; ++j) {
+                const int c = d * C::CPR + j;
+                if (m0 + c < args.M) {
+                  const size_t off = base + (size_t)(m0 + c) * n_out_dim;
+                  const unsigned short hv = (unsigned short)(hp[c >> 1] >> (16 * (c & 1)));
 #pragma unroll 1
-          for (int r = 0; r < args.ar.world; ++r) {
-            __half* dst = reinterpret_cast<__half*>(args.ar.bufs[(args.ar.rank + r) % args.ar.world]) + base + (size_t)m0 * n_out_dim;
-#pragma unroll
-            for (int d = 0; d < kSplit; ++d) {
-              if (kSplit == 1 || d == (int)krank) {        // uniform per CTA: this rank's token columns
-#pragma unroll
-                for (int j = 0; j < C::CPR; ++j) {
-                  const int c = d * C::CPR + j;
-                  if (m0 + c < args.M) ar_st_u16(dst + (size_t)c * n_out_dim, (unsigned short)(hp[c >> 1] >> (16 * (c & 1))));
+                  for (int r = 0; r < args.ar.world; ++r) {
+                    int peer = args.ar.rank + r;
+                    if (peer >= args.ar.world) peer -= args.ar.world;
+                    ar_st_u16(reinterpret_cast<__half*>(args.ar.bufs[peer]) + off, hv);
+                  }
                 }
               }
             }

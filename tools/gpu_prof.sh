@@ -27,12 +27,12 @@ for s in $STEPS; do case $s in
   decode)   timeout 300 ncu $FULL -k regex:batch_decode -s 2 -c 1 -f -o $OUT/prof_decode python tools/layer_bench.py --copies 1 > /dev/null 2>&1 ;;
   quant)    timeout 300 ncu $FULL -k regex:rmsnorm -s 2 -c 1 -f -o $OUT/prof_rmsnorm python tools/layer_bench.py --copies 1 > /dev/null 2>&1 ;;
   layer)    # per-kernel times of one decode step of a Llama-7B layer
-            timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_i4|quant_kernel|decode_kernel|append_kv" --csv \
+            timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_i4|quant_kernel|decode_kernel|append_kv|reorder" --csv \
                 --log-file $OUT/layer_launches.csv python tools/layer_bench.py --copies 2 > /dev/null 2>&1
             python - <<'PY'
 import csv
 rows = [r for r in csv.reader(open('gpurun_out/layer_launches.csv')) if len(r) > 10 and r[0].isdigit()]
-last = rows[-16:]                                   # 16 launches per layer step
+last = rows[-9:]                                    # 9 launches per layer step (round 2: fused q/k/v, gate/up+act, add+norm)
 tot = sum(float(r[-1]) for r in last)
 for r in last:
     print(f"{float(r[-1]) / 1000:8.2f} us {100 * float(r[-1]) / tot:5.1f}%  {r[4].replace('atom::', '').split('(')[0][:60]}")
