@@ -388,7 +388,9 @@ template <bool kO4>
 int gemm_dispatch(const GemmOperands& op, const atom::GemmArgs& args, uint32_t flags, cudaStream_t stream) {
   // up to 128 tokens the weight-stationary orientation wins (4096^2, M=128: 13.9 us as two 64-token tiles vs 21.3 us for one
   // wave of 32 128x128 tiles); from 3 token tiles on the 128x128 kernel is faster
-  const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) || (!(flags & ATOM_GEMM_FORCE_TALL) && op.M <= 128);
+  // (65..128 tokens are two 64-token tiles per channel tile: only while those CTAs still fit one wave of 148 SMs)
+  const bool skinny = (flags & ATOM_GEMM_FORCE_SKINNY) ||
+                      (!(flags & ATOM_GEMM_FORCE_TALL) && (op.M <= 64 || (op.M <= 128 && (op.N + 127) / 128 * 2 <= 148)));
   // <swap, BN, groups per pipeline stage, packed stages, K split, o4, converter warps, epilogue warpgroups>
   if (!skinny) {
     if (flags & ATOM_GEMM_LEGACY_TALL) return launch_gemm<false, 128, 2, 2, 1, kO4, 4, 2>(op, args, stream);
@@ -696,16 +698,17 @@ int atom_batch_decode_i4(void* o, const void* q, const void* kv_data, const void
   atom::KvArgs kv{(uint8_t*)kv_data, (__half2*)kv_param, (const int32_t*)kv_indptr, (const int32_t*)kv_indices,
                   (const int32_t*)last_page_offset, num_layers, layer_idx, num_heads, page_size, batch_size};
   const size_t smem = atom::batch_decode_smem_bytes(page_size);
-  if (page_size <= 32) {
-    if ((rc = ensure_dynamic_smem(atom::batch_decode_kernel<4>, 100 * 1024, "batch_decode_i4"))) return rc;
-  } else {
-    if ((rc = ensure_dynamic_smem(atom::batch_decode_kernel<8>, 100 * 1024, "batch_decode_i4"))) return rc;
-  }
-  if (page_size <= 32)
-    return launch_k("batch_decode_i4", atom::batch_decode_kernel<4>, dim3(batch_size, num_heads), dim3(atom::DEC_THREADS), smem,
-                    (cudaStream_t)stream, (__half*)o, (const __half*)q, kv);
-  return launch_k("batch_decode_i4", atom::batch_decode_kernel<8>, dim3(batch_size, num_heads), dim3(atom::DEC_THREADS), smem,
-                  (cudaStream_t)stream, (__half*)o, (const __half*)q, kv);
+#define ATOM_DECODE(TPL, PG)                                                                                              \
+  do {                                                                                                                    \
+    if ((rc = ensure_dynamic_smem(atom::batch_decode_kernel<TPL, PG>, 100 * 1024, "batch_decode_i4"))) return rc;         \
+    return launch_k("batch_decode_i4", atom::batch_decode_kernel<TPL, PG>, dim3(batch_size, num_heads),                   \
+                    dim3(atom::DEC_THREADS), smem, (cudaStream_t)stream, (__half*)o, (const __half*)q, kv);               \
+  } while (0)
+  if (page_size == 16) ATOM_DECODE(2, 16);      // the two page sizes of the harness / the reference benchmarks: strides as immediates
+  if (page_size == 32) ATOM_DECODE(4, 32);
+  if (page_size <= 32) ATOM_DECODE(4, 0);
+  ATOM_DECODE(8, 0);
+#undef ATOM_DECODE
 }
 
 int atom_append_kv_i4(void* kv_data, void* kv_param, const void* kv_indptr, const void* kv_indices,

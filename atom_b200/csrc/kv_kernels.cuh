@@ -110,12 +110,14 @@ __device__ __forceinline__ float fhfma(__half a, __half b, float acc) {
   return acc;
 }
 
-template <int kMaxTpl>   // tokens per lane per page = P / 8 <= kMaxTpl
+// kMaxTpl: tokens per lane per page = P / 8 <= kMaxTpl.  kP: page size as a compile-time constant (16 / 32: the sizes the harness
+// uses -- all table strides and the token loops become immediates) or 0 = read it from the arguments.
+template <int kMaxTpl, int kP>
 __global__ void __launch_bounds__(DEC_THREADS, 4)
 batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs kv, int pdl) {
   extern __shared__ __align__(128) uint8_t smem_d[];
   if (pdl) { griddep_launch_dependents(); griddep_wait(); }      // q and the newest KV entry come from the preceding kernels
-  const int P = kv.P;
+  const int P = kP ? kP : kv.P;
   const int stage_bytes = 2 * 64 * P + 2 * 4 * P;                   // K | V | K params | V params
   uint8_t* ring = smem_d;
   uint2* tabh = reinterpret_cast<uint2*>(smem_d + DEC_STAGES * stage_bytes);    // [8 couples][P][4 quarters] (cos2, sin2) half2

@@ -46,6 +46,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="override the number of decoder layers (0 = the model's)")
     ap.add_argument("--block-len", type=int, default=32)
     ap.add_argument("--no-cuda-graphs", action="store_true", help="run decode-only steps eagerly too (the reference's way)")
+    ap.add_argument("--warmup-batches", type=int, default=1,
+                    help="untimed request batches served first (first-use costs: lazy kernel loading, attribute calls, graph "
+                         "capture); 0 = time the cold process like the reference's script")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_textgen: needs a CUDA device (the INT4 kernels have no CPU path)")
@@ -61,8 +64,14 @@ def main():
                       tg.pool_capacity(args.batch_size, args.maxlen, args.block_len), args.block_len, device)
     runner = None if args.no_cuda_graphs else tg.DecodeGraphRunner(
         model, pool, device, max_pages_per_seq=(args.maxlen + args.block_len - 1) // args.block_len + 1)
+    if args.warmup_batches > 0:
+        wrs = tg.generate_request_set(args.batch_size * args.warmup_batches, args.maxlen)
+        tg.run_textgen(model, wrs, cfg, pool, device, sync=torch.cuda.synchronize, decode_runner=runner)
+        torch.cuda.synchronize()
+        rs = tg.generate_request_set(args.batch_size * args.num_batches, args.maxlen)     # the generator is seeded: same set as without warm-up
     res = tg.run_textgen(model, rs, cfg, pool, device, sync=torch.cuda.synchronize, decode_runner=runner)
     rep = tg.report(rs, cfg, res)
+    rep["warmup_batches"] = args.warmup_batches
     e, et, d = rep["encode_latency_ms_per_request"], rep["encode_latency_ms_per_token"], rep["decode_latency_ms_per_token"]
     print("num_requests:", rep["num_requests"])
     print("batch_size:", rep["batch_size"])

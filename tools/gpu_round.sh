@@ -19,7 +19,9 @@ for s in $STEPS; do case $s in
   layer)   echo "== decoder-layer decode step"
            timeout 300 python tools/layer_bench.py 2>&1 | tail -1 | tee $OUT/layer_7b.json
            timeout 300 python tools/layer_bench.py --hidden 5120 --inter 13824 --heads 40 --batch 32 --kvlen 1024 --layers 40 2>&1 | tail -1 | tee $OUT/layer_13b.json ;;
-  harness) echo "== continuous-batching harness"; timeout 900 python tools/bench_textgen.py --model 7b --batch-size 16 --num-batches 2 --maxlen 512 2> $OUT/textgen.err | tee $OUT/textgen_7b.txt | tail -9; tail -3 $OUT/textgen.err ;;
+  harness) echo "== continuous-batching harness (warm: one untimed batch first; cold: like the reference's script)"
+           timeout 900 python tools/bench_textgen.py --model 7b --batch-size 16 --num-batches 2 --maxlen 512 2> $OUT/textgen.err | tee $OUT/textgen_7b.txt | tail -2 | cut -c1-900; tail -3 $OUT/textgen.err
+           timeout 900 python tools/bench_textgen.py --model 7b --batch-size 16 --num-batches 2 --maxlen 512 --warmup-batches 0 2>> $OUT/textgen.err | tee $OUT/textgen_7b_cold.txt | tail -2 | cut -c1-900 ;;
   micro)   echo "== microbenchmarks"; for b in microbench sync_bench tma_bench tmem_bench; do timeout 120 ./tools/$b > $OUT/$b.jsonl 2>&1; echo "$b rc=$?"; done ;;
   sk)      echo "== skinny GEMM: probes, parity, timing (PDL on / off, legacy kernel beside it)"
            timeout 300 python tools/gpu_check.py diag 2>&1 | tee $OUT/sk_diag.jsonl | cut -c1-400
@@ -34,12 +36,14 @@ for s in $STEPS; do case $s in
   dec)     echo "== decode attention: parity at 5e-4, timing, ncu capture"
            timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py -m gpu -q --timeout=300 -p no:cacheprovider -k "decode or rmsnorm" > $OUT/pytest_dec.txt 2>&1; echo "rc=$?"; tail -15 $OUT/pytest_dec.txt
            timeout 300 python tools/layer_bench.py 2>&1 | tail -1 | tee $OUT/layer_7b.json
-           timeout 300 ncu --set full --clock-control none --import-source on -k regex:batch_decode -s 2 -c 1 -f -o $OUT/prof_decode python tools/layer_bench.py --copies 1 > /dev/null 2>&1; ls -la $OUT/prof_decode.ncu-rep ;;
-  ncug)    echo "== ncu: prefill GEMM kernels at M=4096 (128x128 and 128x256 tiles), decode GEMM at M=16"
+           ;;
+  ncug)    echo "== ncu --set full: prefill GEMM (128x128) at M=4096, decode GEMM at M=16 (summarised here; the .ncu-rep files are too big to travel)"
            FULL="--set full --clock-control none --import-source on"
            timeout 300 ncu $FULL -k regex:gemm_i4_tall -s 3 -c 1 -f -o $OUT/prof_gemm_m4096_tall128 python tools/prof_gemm.py 4096 1024 > /dev/null 2>&1
-           timeout 300 ncu $FULL -k regex:gemm_i4_wide -s 3 -c 1 -f -o $OUT/prof_gemm_m4096_wide256 python tools/prof_gemm.py 4096 512 > /dev/null 2>&1
            timeout 300 ncu $FULL -k regex:gemm_i4_skinny -s 3 -c 1 -f -o $OUT/prof_gemm_m16_skinny python tools/prof_gemm.py 16 0 > /dev/null 2>&1
-           ls -la $OUT/prof_gemm_*.ncu-rep ;;
+           timeout 300 ncu $FULL -k regex:batch_decode -s 2 -c 1 -f -o $OUT/prof_decode python tools/layer_bench.py --copies 1 > /dev/null 2>&1
+           for f in prof_gemm_m4096_tall128 prof_gemm_m16_skinny prof_decode; do
+             python tools/ncu_summary.py $OUT/$f.ncu-rep $OUT/ncu_$f > /dev/null 2>&1 && echo "summarised $f" && rm -f $OUT/$f.ncu-rep
+           done ;;
   *) echo "unknown step $s" ;;
 esac; done
