@@ -30,6 +30,7 @@ class NcclAllReduce:
 class PushAllReduce:
     name = "push (atom_b200 one-shot kernel over NVLink peer memory)"
     CTAS = 64
+    fuse = True        # tp.py may fold the two halves into the row-parallel GEMM's epilogue and the following add+RMSNorm launch
 
     def __init__(self, max_numel, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem

@@ -43,7 +43,10 @@ enum { EPI_O16 = 0, EPI_O4 = 1, EPI_QKV = 2, EPI_GATEUP = 3, EPI_PUSH = 4 };
 template <int BN, int kSplit, int kEpi>
 struct SkinnyCfg {
   static constexpr int BM = 128;                       // weight rows per tile = TMEM lanes
-  static constexpr bool ONE_PER_SM = BN == 64;         // 64 accumulators per thread need > 80 registers
+  // One CTA per SM: 64 accumulators per thread need > 80 registers; and the fused q/k/v grid (3 H / 128 tiles: 96 at Llama-7B)
+  // never fills 148 SMs twice, cannot split K (o4 tiles) and is bound by the bytes it keeps in flight: a 16-deep weight ring
+  // instead of 6 (Little: 96 CTAs x 48 KB / ~1.5 us = 3 TB/s at best; measured 1.35 TB/s, 18.6 us for 25 MB).
+  static constexpr bool ONE_PER_SM = BN == 64 || kEpi == EPI_QKV;
   static constexpr int TMEM_COLS = ONE_PER_SM ? 512 : 256;
   // The unit of every hand-off (converter -> MMA -> epilogue) is a PAIR of quantisation groups: a wait on an mbarrier
   // costs ~100 cycles even when the phase has completed and a tcgen05.commit ~200 cycles of the single issuing thread,
@@ -52,7 +55,7 @@ struct SkinnyCfg {
   static constexpr int A_PAIRS = ONE_PER_SM ? 4 : (BN == 16 ? 3 : 2);   // tensor-memory operand slots (2 groups = 64 columns each)
   static constexpr int ACC_PAIRS = 2;                  // accumulator slots (2 groups = 2 * BN columns each)
   static constexpr int A_COL0 = 0, ACC_COL0 = A_PAIRS * 64;
-  static constexpr int PACK = ONE_PER_SM ? 8 : (BN == 16 ? 6 : (kEpi == EPI_GATEUP ? 4 : 5));   // packed weight ring depth (groups)
+  static constexpr int PACK = (kEpi == EPI_QKV && BN <= 32) ? 16 : (ONE_PER_SM ? 8 : (BN == 16 ? 6 : (kEpi == EPI_GATEUP ? 4 : 5)));   // packed weight ring depth (groups)
   static constexpr int QB = 4, QS = 2 * QB;            // token tiles: groups per hand-off, expanded slots
   static constexpr int SC = BN == 16 ? 32 : 16;        // groups per staged scale chunk
   static constexpr int THREADS = 384;                  // 4 service warps, 4 converter warps, 4 epilogue warps
@@ -558,47 +561,47 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       }
       if (warp == 8 && lane == 0) trace_stamp(args, 3);
       const int n = tile * C::BM + row;
-      if (n < n_out_dim && n0 + row < args.N) {
-        if constexpr (kEpi == EPI_PUSH) {
-          // fused all-reduce, push half: D goes to slot [call % 3][rank] of EVERY rank's receive buffer (-0.0, the buffers'
-          // "not yet arrived" pattern, travels as +0.0); the following add+RMSNorm kernel polls and sums the slots
-          const uint32_t cur = (ar_ld_state(args.ar.state) + 1) % 3;
-          const size_t base = ((size_t)cur * args.ar.world + args.ar.rank) * (size_t)args.ar.slot + n;
-          uint32_t hp[BN / 2];                 // the FP16 results first: the accumulators are dead before the peer loop
+      if constexpr (kEpi == EPI_PUSH) {
+        // fused all-reduce, push half: this rank's CPR token rows of the tile go to slot [call % 3][rank] of EVERY rank's receive
+        // buffer (-0.0, the buffers' "not yet arrived" pattern, travels as +0.0); the following add+RMSNorm kernel polls and
+        // sums the slots.  The tile is transposed through the (now idle) packed-weight ring so that the peer stores are 16 bytes
+        // of 8 consecutive channels: 2-byte stores over NVLink cost an order of magnitude more per byte.
+        __half* stg = reinterpret_cast<__half*>(smem + C::OFF_PACK_P);         // [CPR tokens][128 channels]
 #pragma unroll
-          for (int c = 0; c < BN; c += 2) {
-            unsigned short h0 = __half_as_ushort(__float2half_rn(acc[c] * kInv)), h1 = __half_as_ushort(__float2half_rn(acc[c + 1] * kInv));
-            if (h0 == 0x8000u) h0 = 0;
-            if (h1 == 0x8000u) h1 = 0;
-            hp[c >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-          }
-          // peer loop innermost and not unrolled: one live address at a time (this is tail code, registers are scarce here)
+        for (int d = 0; d < kSplit; ++d) {
+          if (kSplit == 1 || d == (int)krank) {            // uniform per CTA
 #pragma unroll
-          for (int d = 0; d < kSplit; ++d) {
-            if (kSplit == 1 || d == (int)krank) {          // uniform per CTA: this rank's token columns
-#pragma unroll
-              for (int j = 0; j < C::CPR; ++j) {
-                const int c = d * C::CPR + j;
-                if (m0 + c < args.M) {
-                  const size_t off = base + (size_t)(m0 + c) * n_out_dim;
-                  const unsigned short hv = (unsigned short)(hp[c >> 1] >> (16 * (c & 1)));
-#pragma unroll 1
-                  for (int r = 0; r < args.ar.world; ++r) {
-                    int peer = args.ar.rank + r;
-                    if (peer >= args.ar.world) peer -= args.ar.world;
-                    ar_st_u16(reinterpret_cast<__half*>(args.ar.bufs[peer]) + off, hv);
-                  }
-                }
-              }
+            for (int j = 0; j < C::CPR; ++j) {
+              unsigned short hv = __half_as_ushort(__float2half_rn(acc[d * C::CPR + j] * kInv));
+              if (hv == 0x8000u) hv = 0;
+              stg[j * C::BM + row] = __ushort_as_half(hv);
             }
           }
-        } else {
-#pragma unroll
-          for (int c = 0; c < BN; ++c) {
-            const int m = m0 + c;
-            if ((kSplit == 1 || c / C::CPR == (int)krank) && m < args.M)
-              args.d[(size_t)m * n_out_dim + n] = __float2half_rn(acc[c] * kInv);      // a warp writes 64-B runs
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t cur = (ar_ld_state(args.ar.state) + 1) % 3;
+        const size_t base = ((size_t)cur * args.ar.world + args.ar.rank) * (size_t)args.ar.slot;
+        const int pt = (warp - 8) * 32 + lane;
+        for (int q = pt; q < C::CPR * 16; q += 128) {
+          const int j = q >> 4, piece = q & 15;
+          const int m = m0 + (int)krank * C::CPR + j, nn = n0 + piece * 8;
+          if (m < args.M && nn < args.N) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + j * C::BM + piece * 8);
+            const size_t off = base + (size_t)m * n_out_dim + nn;
+#pragma unroll 1
+            for (int r = 0; r < args.ar.world; ++r) {
+              int peer = args.ar.rank + r;
+              if (peer >= args.ar.world) peer -= args.ar.world;
+              ar_st_v4(reinterpret_cast<__half*>(args.ar.bufs[peer]) + off, v);
+            }
           }
+        }
+      } else if (n < n_out_dim && n0 + row < args.N) {
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          const int m = m0 + c;
+          if ((kSplit == 1 || c / C::CPR == (int)krank) && m < args.M)
+            args.d[(size_t)m * n_out_dim + n] = __float2half_rn(acc[c] * kInv);      // a warp writes 64-B runs
         }
       }
     } else {

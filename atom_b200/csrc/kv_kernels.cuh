@@ -278,7 +278,10 @@ batch_decode_kernel(__half* __restrict__ o, const __half* __restrict__ q, KvArgs
       }
     }
     // ---- one rescale per page, then p * v with the dequant folded; V partial sums of the page in half2
-    const float m_new = fmaxf(m, xmax);
+    // The running maximum only moves when it is exceeded by more than 2^6: any m gives the same softmax, the weights then reach
+    // at most 64 (times the V scale: far inside FP16 for the per-page half2 sums), and with 32 lanes per warp "some lane saw a new
+    // maximum" would otherwise be true on almost every page -- the 34-FMUL rescale below now runs a few times per sequence.
+    const float m_new = (xmax > m + 6.f) ? xmax : m;
     const float sc = exp2f(m - m_new);
     m = m_new;
     if (__any_sync(0xffffffffu, sc != 1.f)) {     // once the running maxima have settled no lane of the warp rescales

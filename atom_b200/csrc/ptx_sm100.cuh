@@ -256,27 +256,36 @@ __device__ __forceinline__ uint32_t ar_strip_sentinel(uint32_t w) {
   if ((w >> 16) == 0x8000u) w &= 0x0000FFFFu;
   return w;
 }
-// one 16-byte chunk of the sum: poll the `world` slots in local memory until the payload is there, add in rank order (FP32)
+// one 16-byte chunk of the sum: the loads of up to 8 ranks' slots are in flight together (a dependent chain of `world` volatile
+// loads per chunk is what an earlier revision spent most of its time in), each is re-polled until its payload is there, and the
+// sum is formed in rank order in FP32
 __device__ __forceinline__ uint4 ar_reduce_chunk(const uint4* local_cur, long long slot_chunks, long long i, int world, unsigned long long& t0) {
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  for (int r = 0; r < world; ++r) {
-    const uint4* src = local_cur + (long long)r * slot_chunks + i;
-    uint4 v = ar_ld_v4(src);
-    // bounded: a peer that never arrives (crashed rank, mismatched call sequence) traps after ~4 s instead of hanging the GPU
-    for (uint32_t spins = 0; ar_has_sentinel(v); ++spins) {
-      if ((spins & 0x3FFu) == 0x3FFu) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000ull) asm volatile("trap;");
-      }
-      v = ar_ld_v4(src);
-    }
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
+  for (int r0 = 0; r0 < world; r0 += 8) {
+    uint4 v[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+    for (int x = 0; x < 8; ++x)
+      if (r0 + x < world) v[x] = ar_ld_v4(local_cur + (long long)(r0 + x) * slot_chunks + i);
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      if (r0 + x < world) {
+        // bounded: a peer that never arrives (crashed rank, mismatched call sequence) traps after ~4 s instead of hanging the GPU
+        for (uint32_t spins = 0; ar_has_sentinel(v[x]); ++spins) {
+          if ((spins & 0x3FFu) == 0x3FFu) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) asm volatile("trap;");
+          }
+          v[x] = ar_ld_v4(local_cur + (long long)(r0 + x) * slot_chunks + i);
+        }
+        const __half2* h = reinterpret_cast<const __half2*>(&v[x]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+      }
+    }
   }
   uint4 o;
   __half2* oh = reinterpret_cast<__half2*>(&o);

@@ -105,13 +105,17 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ re
   // independent loads first: the first group's reorder indices and the weight row travel while the row is reduced
   short4 id_next = (warp < ng) ? *reinterpret_cast<const short4*>(idx + warp * 128 + lane * 4) : make_short4(0, 0, 0, 0);
   float sumv = 0.f;
+  if (kReduce) {      // all 16 warps form the all-reduced row in shared memory first (2 chunks per thread at hidden = 8192)
+    for (int ci = tid; ci < hidden / 8; ci += QUANT_THREADS)
+      reinterpret_cast<uint4*>(xs)[ci] = ar_reduce_chunk(ar_local, ar.slot / 8, (long long)row * (hidden / 8) + ci, ar.world, ar_t0);
+    __syncthreads();
+  }
   if (tid >= 128) {
     for (int i = tid - 128; i < hidden / 8; i += QUANT_THREADS - 128)
       reinterpret_cast<uint4*>(ws)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(w) + i);
   } else if ((ept & 7) == 0) {
     for (int i = 0; i < ept; i += 8) {
-      uint4 u = kReduce ? ar_reduce_chunk(ar_local, ar.slot / 8, ((long long)row * hidden + tid * ept + i) / 8, ar.world, ar_t0)
-                                    : *reinterpret_cast<const uint4*>(xr + tid * ept + i);
+      uint4 u = kReduce ? *reinterpret_cast<const uint4*>(xs + tid * ept + i) : *reinterpret_cast<const uint4*>(xr + tid * ept + i);
       if (residual != nullptr) {
         const uint4 rr = *reinterpret_cast<const uint4*>(residual + (size_t)row * hidden + tid * ept + i);
         __half2* hu = reinterpret_cast<__half2*>(&u);

@@ -72,7 +72,8 @@ class RowParallelLinearInt4(nn.Module):
 
     def can_push(self, batch):
         """Fused all-reduce (GEMM epilogue pushes, the following add+RMSNorm reduces): push kernel, decode batch, wide rows."""
-        return (self.world > 1 and self.gemm_fn is None and getattr(self.allreduce, "handle", None) is not None and batch <= 64
+        return (self.world > 1 and self.gemm_fn is None and getattr(self.allreduce, "handle", None) is not None
+                and getattr(self.allreduce, "fuse", False) and batch <= 64
                 and self.local.out_features % 1024 == 0 and batch * self.local.out_features <= self.allreduce.slot)
 
     def forward_push(self, local_tuple):

@@ -112,7 +112,9 @@ hidden, inter, heads, batch, kvlen, page = 4096, 11008, 32, 16, 300, 16
 cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads, num_hidden_layers=1)
 lh = heads // world
 outs = []
-for ar in (PushAllReduce(batch * hidden, dev), NcclAllReduce()):
+unfused = PushAllReduce(batch * hidden, dev)
+unfused.fuse = False                    # same kernel pieces, but GEMM -> stand-alone all-reduce kernel -> add+RMSNorm
+for ar in (PushAllReduce(batch * hidden, dev), unfused, NcclAllReduce()):
     layers = [TPLlamaDecoderLayer(cfg, 0, rank, world, allreduce=ar).to(dev).init_random(5 + i) for i in range(2)]
     kvs = []
     for i in range(2):
@@ -133,9 +135,13 @@ for ar in (PushAllReduce(batch * hidden, dev), NcclAllReduce()):
         print(json.dumps({"fused_allreduce_in_use": bool(layers[0].o_proj.can_push(batch))}), flush=True)
     outs.append(y.float())
     torch.cuda.synchronize()
-d = (outs[0] - outs[1]).abs().max().item()
-scale = outs[1].abs().max().item()
-report("tp_layer_push_vs_nccl", d <= 2e-2 * max(1.0, scale) and bool(torch.isfinite(outs[0]).all()), max_abs_diff=d, out_absmax=scale)
+# fused and stand-alone push all-reduce form the same rank-order FP32 sums: bit-identical layer outputs
+report("tp_layers_fused_equals_unfused_push", torch.equal(outs[0], outs[1]), max_abs_diff=(outs[0] - outs[1]).abs().max().item())
+# NCCL sums in another order and precision; two quantised layers amplify that (an INT4 code flips here and there)
+d = (outs[0] - outs[2]).abs().max().item()
+scale = outs[2].abs().max().item()
+rel = ((outs[0] - outs[2]).norm() / outs[2].norm()).item()
+report("tp_layers_push_vs_nccl", rel <= 2e-2 and bool(torch.isfinite(outs[0]).all()), max_abs_diff=d, out_absmax=scale, rel_l2=rel)
 # all ranks must hold the same (replicated) hidden state
 ref = outs[0].clone()
 dist.broadcast(ref, 0)
