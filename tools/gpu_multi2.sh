@@ -4,9 +4,8 @@ OUT=gpurun_out; mkdir -p $OUT
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 echo "== pytest (all-reduce, fused ops, gemm parity)"
 timeout 900 python -m pytest tests -m gpu -q -x --timeout=300 -p no:cacheprovider > $OUT/pytest.txt 2>&1; echo "rc=$?"; tail -8 $OUT/pytest.txt
-echo "== upload / PDL race probe"
-timeout 200 python tools/flaky_check.py 2>&1 | tail -3 | tee $OUT/flaky.jsonl
-ATOM_B200_GEMM_PDL=0 timeout 200 python tools/flaky_check.py 2>&1 | tail -3 | tee -a $OUT/flaky.jsonl
+echo "== layer decode step (1 GPU)"
+timeout 300 python tools/layer_bench.py 2>&1 | tail -1 | tee $OUT/layer_7b.json | cut -c1-300
 echo "== tp_check"
 timeout 240 $RUN --master-port 29516 tools/tp_check.py 2> $OUT/tp_check_n2.err | tee $OUT/tp_check_n2.jsonl | cut -c1-300
 echo "rc=${PIPESTATUS[0]}"; grep -v Warning $OUT/tp_check_n2.err | tail -5
