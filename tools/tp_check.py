@@ -115,6 +115,7 @@ outs = []
 unfused = PushAllReduce(batch * hidden, dev)
 unfused.fuse = False                    # same kernel pieces, but GEMM -> stand-alone all-reduce kernel -> add+RMSNorm
 for ar in (PushAllReduce(batch * hidden, dev), unfused, NcclAllReduce()):
+    torch.manual_seed(31337)            # the layers draw their reorder permutations from the global generator: same layers in every run
     layers = [TPLlamaDecoderLayer(cfg, 0, rank, world, allreduce=ar).to(dev).init_random(5 + i) for i in range(2)]
     kvs = []
     for i in range(2):
