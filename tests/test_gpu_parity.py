@@ -257,6 +257,11 @@ def test_fused_gateup_activation_equals_three_calls(m, inter, k):
     b, bs, bk, bks = _concat_weights(ws)
     got = ops.dense_layer_gemm_i4_gateup_act(act[0], T(b), act[1], T(bs), act[2], T(bk), act[3], T(bks))
     assert torch.equal(got[0], ref[0]), "INT8 outliers differ"
-    assert torch.equal(got[1], ref[1]), "packed INT4 differs"
+    if not torch.equal(got[1], ref[1]):        # say where: a whole tile (hand-off / launch problem) or single codes (arithmetic)
+        bad = (got[1] != ref[1]).nonzero()
+        cols = sorted(set((bad[:, 1] // 64).tolist()))
+        raise AssertionError(f"packed INT4 differs: {bad.shape[0]} bytes, rows {sorted(set(bad[:, 0].tolist()))[:8]}, "
+                             f"channel tiles {cols[:12]} ({len(cols)} tiles), first {bad[0].tolist()}: "
+                             f"{int(got[1][tuple(bad[0])])} vs {int(ref[1][tuple(bad[0])])}")
     sel = torch.tensor([O.scale_index(r) + 2 * j for r in range(m) for j in range(4)], device="cuda:0")
     assert torch.equal(got[2][sel], ref[2][sel]) and torch.equal(got[3][:, sel], ref[3][:, sel]), "scales differ"
