@@ -58,7 +58,11 @@ struct SkinnyCfg {
   static constexpr int PACK = (kEpi == EPI_QKV && BN <= 32) ? 16 : (ONE_PER_SM ? 8 : (BN == 16 ? 6 : (kEpi == EPI_GATEUP ? 4 : 5)));   // packed weight ring depth (groups)
   static constexpr int QB = 4, QS = 2 * QB;            // token tiles: groups per hand-off, expanded slots
   static constexpr int SC = BN == 16 ? 32 : 16;        // groups per staged scale chunk
-  static constexpr int THREADS = 384;                  // 4 service warps, 4 converter warps, 4 epilogue warps
+  // 4 service warps, 4 converter warps, 4 epilogue warps; the one-CTA-per-SM instances add a second converter warpgroup
+  // (warps 12-15, the unit's second group): a 33-group chain without a K split is paced by the converters (~650 cycles per
+  // group with 4 warps, tools/microbench), and with one CTA per SM the registers for 16 warps are there
+  static constexpr int CONV_WGS = ONE_PER_SM ? 2 : 1;
+  static constexpr int THREADS = 384 + 128 * (CONV_WGS - 1);
   static constexpr int PACK_P = BM * 64;
   static constexpr int EXP_Q = (BN * 128 + 1023) / 1024 * 1024;
   static constexpr int CPR = kEpi == EPI_GATEUP ? BN : BN / kSplit;   // token columns reduced + stored by one split-K rank (gate/up: all of them go to rank 0)
@@ -201,7 +205,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
     __syncwarp();
   } else if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::PACK; ++i) mbar_init(&pack_empty[i], 4);
-    for (int i = 0; i < C::A_PAIRS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&mma_done[i], 1); }
+    for (int i = 0; i < C::A_PAIRS; ++i) { mbar_init(&a_full[i], 4 * C::CONV_WGS); mbar_init(&mma_done[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&qx_full[i], 2); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < C::ACC_PAIRS; ++i) mbar_init(&acc_empty[i], 4);
     mbar_init(kq_full, 2);
@@ -339,15 +343,17 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       __syncwarp();
       if (lane == 0) mbar_arrive(kq_full);
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ============================================================ weight converters: thread = weight row
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+    // ============================================================ weight converters: thread = weight row; with two converter
+    // warpgroups, warps 4-7 take the first group of every unit and warps 12-15 the second
     const int wq = warp & 3, row = wq * 32 + lane, t = (warp - 4) * 32 + lane;
+    const int jsel = warp >= 12 ? 1 : 0;
     const int xr = (row >> 1) & 3;                       // SWIZZLE_64B: 16-B chunk index ^= address bits [7,9)
     for (int u = 0; u < np4; ++u) {
       const int ar = u % C::A_PAIRS, ng = min(2, n4 - 2 * u);
       if (u >= C::A_PAIRS) mbar_wait(&mma_done[ar], ((u / C::A_PAIRS) - 1) & 1);
       if (t == 0 && u < 8) trace_stamp(args, 24 + u);
-      for (int j = 0; j < ng; ++j) {
+      for (int j = (C::CONV_WGS == 2 ? jsel : 0); j < (C::CONV_WGS == 2 ? min(ng, jsel + 1) : ng); ++j) {
         const int i = 2 * u + j, ps = i % C::PACK;
         mbar_wait(&pack_full[ps], (i / C::PACK) & 1);
         if (t == 0 && u < 8 && j == 0) trace_stamp(args, 40 + u);
@@ -376,7 +382,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       if (lane == 0) mbar_arrive(&a_full[ar]);
       if (t == 0 && u < 8) trace_stamp(args, 72 + u);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ============================================================ epilogue: thread = output channel (TMEM lane)
     const int wq = warp & 3, row = wq * 32 + lane, te = (warp - 8) * 32 + lane;
     float acc[BN];
@@ -643,7 +649,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   // ---------------------------------------------------------------- teardown
   // split-K: this CTA's shared memory is a target only until red_full completed (the epilogue waited for it), so no
   // closing cluster barrier is needed; every thread still pairs its setup arrive with one wait.
-  if constexpr (kSplit > 1) { if (warp < 8) cluster_wait(); }
+  if constexpr (kSplit > 1) { if (warp < 8 || warp >= 12) cluster_wait(); }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
