@@ -27,10 +27,27 @@ def run_case(m, inter, k, reps):
     torch.cuda.synchronize()
     def nd(xs, idx=None):
         return [int((xs[0][idx] != x[idx]).sum()) if idx is not None else int((xs[0] != x).sum()) for x in xs[1:]]
-    return {"case": [m, inter, k], "gate_gemm_vs_first": nd(gs), "up_gemm_vs_first": nd(us), "ref_int4_vs_first": nd(refs, 1),
+    detail = None
+    for fi, (f, r) in enumerate(zip(fused, refs)):
+        if not torch.equal(f[1], r[1]):
+            bad = (f[1] != r[1]).nonzero()
+            tiles = sorted(set((bad[:, 1] // 64).tolist()))
+            row0, tile0 = int(bad[0, 0]), int(bad[0, 1]) // 64
+            G = f[3].shape[0]
+            detail = {"fused_index": fi, "bad_bytes": int(bad.shape[0]), "tiles": tiles[:10], "rows": sorted(set(bad[:, 0].tolist())),
+                      "int8_mismatch": int((f[0] != r[0]).sum()), "keeper_scale_mismatch": int((f[2] != r[2]).sum()),
+                      "group_scale_mismatch": int((f[3] != r[3]).sum()),
+                      "scale_rows_bad": sorted(set((f[3] != r[3]).nonzero()[:, 0].tolist()))[:10],
+                      "first": {"row": row0, "tile": tile0,
+                                "got": f[1][row0, tile0 * 64:(tile0 + 1) * 64].cpu().numpy().astype(np.uint8).tolist(),
+                                "ref": r[1][row0, tile0 * 64:(tile0 + 1) * 64].cpu().numpy().astype(np.uint8).tolist(),
+                                "got_scale": [float(x) for x in f[3][tile0].float().cpu().numpy()[:8]],
+                                "ref_scale": [float(x) for x in r[3][tile0].float().cpu().numpy()[:8]]}}
+            break
+    return {"case": [m, inter, k], "detail": detail, "gate_gemm_vs_first": nd(gs), "up_gemm_vs_first": nd(us), "ref_int4_vs_first": nd(refs, 1),
             "fused_int4_vs_first": nd(fused, 1), "fused_vs_ref_int4": [int((f[1] != r[1]).sum()) for f, r in zip(fused, refs)]}
 
-for rnd in range(4):
+for rnd in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     for case in [(16, 256, 512), (5, 384, 1024), (32, 512, 1024), (64, 256, 512)]:
         run_case(*case, reps=1)
     print(json.dumps(run_case(16, 11008, 4096, reps=4)), flush=True)

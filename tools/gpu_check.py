@@ -256,8 +256,8 @@ if __name__ == "__main__":
                 rec[name] = round(us, 2)
             print(json.dumps(rec), flush=True)
             del sets
-    elif cmd == "trace":
-        trace(int(sys.argv[2]), int(sys.argv[3]))
+    elif cmd == "trace":       # trace M FLAGS [N K]
+        trace(int(sys.argv[2]), int(sys.argv[3]), *[int(x) for x in sys.argv[4:6]])
     elif cmd == "tracew":
         trace_warm(int(sys.argv[2]), int(sys.argv[3]))
     elif cmd == "time":
