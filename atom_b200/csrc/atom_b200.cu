@@ -624,7 +624,6 @@ int atom_gemm_i4_gateup_act(const void* a, const void* b_gu, const void* a_scale
                                               "run the two projections and activate_fp16_i4 for M=%lld", (long long)M);
   GemmOperands op{a, b_gu, a_keeper, b_keeper_gu, M, 2 * I, K};
   atom::GemmArgs args{};
-  { const char* e = getenv("ATOM_B200_DBG"); args.dbg = e ? atoi(e) : 0; }
   args.a_scale = (const __half*)a_scale; args.a_keeper_scale = (const __half*)a_keeper_scale;
   args.b_scale = (const __half*)b_scale_gu; args.b_keeper_scale = (const __half*)b_keeper_scale_gu;
   args.M = (int)M; args.N = (int)(2 * I); args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M); args.trace = g_trace;

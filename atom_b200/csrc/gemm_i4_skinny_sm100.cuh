@@ -402,7 +402,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
           const int gi = c >> 4, part = c & 15, g = g_begin + i0 + gi;
           const __half* bs_row = (g == args.G) ? args.b_keeper_scale : args.b_scale + (size_t)g * args.ldb_scale;
           uint4 v = make_uint4(0, 0, 0, 0);
-          if (n0 + 8 * part < (kEpi == EPI_GATEUP ? args.gu_rows : args.N)) v = ld_nc_v4(bs_row + wrow0 + 8 * part);
+          if (n0 + 8 * part < (kEpi == EPI_GATEUP ? args.gu_rows : args.N)) v = ld_cg_v4(bs_row + wrow0 + 8 * part);
           reinterpret_cast<uint4*>(sb_s)[c] = v;
         }
         if (u == 0) griddep_wait();
@@ -472,18 +472,15 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
       cluster_wait();                        // pairs with the setup arrive: both CTAs of the pair are running
       if (krank == 1) {
         // ---------------------------------------------------------- up tile: hand the FP32 sums to the gate CTA
-        if (args.dbg & 8) { for (int z = 0; z < 40; ++z) __nanosleep(500); }
         const uint32_t remote = mapa_shared(smem_u32(smem + C::OFF_RED), 0) + row * (BN * 4);
         const uint32_t rbar = mapa_shared(smem_u32(red_full), 0);
 #pragma unroll
         for (int c = 0; c < BN; c += 4) st_async_v4(remote + c * 4, acc[c], acc[c + 1], acc[c + 2], acc[c + 3], rbar);
       } else {
-        if (args.dbg & 16) { for (int z = 0; z < 40; ++z) __nanosleep(500); }
         // ---------------------------------------------------------- gate tile: SiLU(gate) * up, then the dynamic
         // quantisation of activate_fp16_i4 (Activate.cuh:102-166) for this 128-channel group of every token.  Both
         // projections are rounded to FP16 first, as they are when the reference stores them between the kernels.
         mbar_wait(red_full, 0);
-        if (args.dbg & 2) { asm volatile("fence.acq_rel.cluster;" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
         const float* red = reinterpret_cast<const float*>(smem + C::OFF_RED);
         float* xmx = reinterpret_cast<float*>(smem + C::OFF_XCH);   // [4 warps][BN]
         const bool last = ((int)blockIdx.x == args.gu_rows / 128 - 1);          // the INT8 keeper group of the down projection
@@ -655,7 +652,6 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   if constexpr (kSplit > 1) { if (warp < 8 || warp >= 12) cluster_wait(); }
   tc_fence_before();
   __syncthreads();
-  if constexpr (kEpi == EPI_GATEUP) { if (args.dbg & 1) { cluster_arrive(); cluster_wait(); } }   // experiment: the up CTA outlives the hand-off
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
   if (threadIdx.x == 0) trace_stamp(args, 4);
 }

@@ -232,7 +232,7 @@ gemm_i4_tall_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT4 
               const int w = lane + 32 * h, blk = w >> 3, i = w & 7;
               if (m0 + 16 * blk + i < args.M) aw[j][h] = ld_cg_u32(as_row + 64 * (m0 / 16 + blk) + 8 * i);
             }
-            if (lane < 16 && n0 + 8 * lane < args.N) bw[j] = ld_nc_v4(bs_row + n0 + 8 * lane);
+            if (lane < 16 && n0 + 8 * lane < args.N) bw[j] = ld_cg_v4(bs_row + n0 + 8 * lane);
           }
         }
         if (s >= C::SCALE_STAGES) mbar_wait(&scale_empty[ss], ((s / C::SCALE_STAGES) - 1) & 1);

@@ -164,7 +164,7 @@ gemm_i4_wide_kernel(const __grid_constant__ CUtensorMap tm_a4,   // packed INT4 
           if (m0 + 16 * blk + i < args.M) aw[x] = ld_cg_u32(as_row + 64 * (m0 / 16 + blk) + 8 * i);
         }
         uint4 bw = make_uint4(0, 0, 0, 0);               // lane l: channels n0 + 8 l .. + 7 (32 lanes cover the 256 channels)
-        if (n0 + 8 * lane < args.N) bw = ld_nc_v4(bs_row + n0 + 8 * lane);
+        if (n0 + 8 * lane < args.N) bw = ld_cg_v4(bs_row + n0 + 8 * lane);
         if (g >= C::SCALE_STAGES) mbar_wait(&scale_empty[ss], ((g / C::SCALE_STAGES) - 1) & 1);
         uint8_t* slot = smem + C::OFF_SM + ss * C::SCALE_BYTES;
         reinterpret_cast<uint32_t*>(slot)[lane] = aw[0];

@@ -61,7 +61,7 @@ reorder_quant_kernel(const __half* __restrict__ x, const int16_t* __restrict__ i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ng = hidden / 128;
   short4 id_next = (warp < ng) ? *reinterpret_cast<const short4*>(idx + warp * 128 + lane * 4) : make_short4(0, 0, 0, 0);
   const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * hidden);
-  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) reinterpret_cast<uint4*>(xs)[i] = ld_nc_v4(src + i);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) reinterpret_cast<uint4*>(xs)[i] = ld_cg_v4(src + i);
   __syncthreads();
   for (int g = warp; g < ng; g += QUANT_WARPS) {
     const short4 id = id_next;
@@ -112,7 +112,7 @@ rmsnorm_quant_kernel(const __half* __restrict__ x, const __half* __restrict__ re
   }
   if (tid >= 128) {
     for (int i = tid - 128; i < hidden / 8; i += QUANT_THREADS - 128)
-      reinterpret_cast<uint4*>(ws)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(w) + i);
+      reinterpret_cast<uint4*>(ws)[i] = ld_cg_v4(reinterpret_cast<const uint4*>(w) + i);
   } else if ((ept & 7) == 0) {
     for (int i = 0; i < ept; i += 8) {
       uint4 u = kReduce ? *reinterpret_cast<const uint4*>(xs + tid * ept + i) : *reinterpret_cast<const uint4*>(xr + tid * ept + i);
