@@ -222,6 +222,11 @@ int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
   cfg.gridDim = dim3((unsigned)((op.N + ch_tile - 1) / ch_tile), (unsigned)((op.M + tok_tile - 1) / tok_tile), kSplit);
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  if (kEpi == atom::EPI_GATEUP && (args.dbg & 2) && C::SMEM_BYTES < 120 * 1024) {     // experiment: one CTA per SM
+    static bool raised = false;
+    if (!raised) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024); raised = true; }
+    cfg.dynamicSmemBytes = 120 * 1024;
+  }
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -624,6 +629,7 @@ int atom_gemm_i4_gateup_act(const void* a, const void* b_gu, const void* a_scale
                                               "run the two projections and activate_fp16_i4 for M=%lld", (long long)M);
   GemmOperands op{a, b_gu, a_keeper, b_keeper_gu, M, 2 * I, K};
   atom::GemmArgs args{};
+  { const char* e = getenv("ATOM_B200_GU_MODE"); args.dbg = e ? atoi(e) : 0; }
   args.a_scale = (const __half*)a_scale; args.a_keeper_scale = (const __half*)a_keeper_scale;
   args.b_scale = (const __half*)b_scale_gu; args.b_keeper_scale = (const __half*)b_keeper_scale_gu;
   args.M = (int)M; args.N = (int)(2 * I); args.G = (int)(K / 128 - 1); args.lda_scale = atom::scale_size((int)M); args.trace = g_trace;

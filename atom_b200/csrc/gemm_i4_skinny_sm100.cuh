@@ -652,6 +652,7 @@ gemm_i4_skinny_kernel(const __grid_constant__ CUtensorMap tm_p4,   // packed INT
   if constexpr (kSplit > 1) { if (warp < 8 || warp >= 12) cluster_wait(); }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kEpi == EPI_GATEUP) { if (args.dbg & 1) { cluster_arrive(); cluster_wait(); } }   // the up CTA outlives the hand-off
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
   if (threadIdx.x == 0) trace_stamp(args, 4);
 }

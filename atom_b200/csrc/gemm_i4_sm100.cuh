@@ -50,6 +50,7 @@ struct GemmArgs {
   const int8_t* a8;              //   reads the (tiny) token operand straight from global memory instead of through TMA
   int pdl;                       // launched with programmatic stream serialization: weights may be fetched before the
                                  // preceding kernel has finished, everything that reads activations waits (griddepcontrol)
+  int dbg;                       // ATOM_B200_GU_MODE experiment bits (gate/up hand-off), 0 in production
   ArArgs ar;                     // row-parallel projection (tp.py): ar.bufs != null => the decode kernel's o16 epilogue stores D
                                  // into slot [call % 3][rank] of every rank's receive buffer instead of d (push half of the
                                  // all-reduce, comm_kernels.cuh); the consumer is rmsnorm_quant_kernel's reducing variant
