@@ -222,11 +222,6 @@ int launch_gemm(const GemmOperands& op, const atom::GemmArgs& args, cudaStream_t
   cfg.gridDim = dim3((unsigned)((op.N + ch_tile - 1) / ch_tile), (unsigned)((op.M + tok_tile - 1) / tok_tile), kSplit);
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  if (kEpi == atom::EPI_GATEUP && (args.dbg & 2) && C::SMEM_BYTES < 120 * 1024) {     // experiment: one CTA per SM
-    static bool raised = false;
-    if (!raised) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024); raised = true; }
-    cfg.dynamicSmemBytes = 120 * 1024;
-  }
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -271,6 +266,11 @@ int launch_skinny(const GemmOperands& op, const atom::GemmArgs& args, cudaStream
   cfg.gridDim = dim3((unsigned)((chan + C::BM - 1) / C::BM), (unsigned)((op.M + BN - 1) / BN), kSplit);
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  if (kEpi == atom::EPI_GATEUP && (args.dbg & 2) && C::SMEM_BYTES < 120 * 1024) {     // experiment: one CTA per SM
+    static bool raised = false;
+    if (!raised) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024); raised = true; }
+    cfg.dynamicSmemBytes = 120 * 1024;
+  }
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
