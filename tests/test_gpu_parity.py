@@ -246,8 +246,8 @@ def test_fused_qkv_equals_three_projections(m, h, k):
 
 # KNOWN ISSUE: at the Llama-7B size (172 CTAs, two resident per SM) the FIRST such launch of a process sometimes
 # returns 1-3 of the 86 channel tiles with slightly different sums (INT4 codes off by one, scales off by a few per cent); later launches
-# and the whole reference path are stable.  Seen in 1 of 3 stress runs on some boxes, never in the full-suite order, never with one CTA
-# per SM (ATOM_B200_GU_MODE=2); not fixed by fences or a closing cluster barrier.  Non-strict xfail keeps the rest of the suite running.
+# and the whole reference path are stable.  Seen in 2 of 4 stress runs on the last box, never in the full-suite order, not with one
+# CTA per SM (ATOM_B200_GU_MODE=2: 0 of 4); not fixed by fences or a closing cluster barrier.  Non-strict xfail keeps the suite running.
 _GATEUP_7B = pytest.param(16, 11008, 4096, marks=pytest.mark.xfail(strict=False, reason="first co-resident launch of the fused gate/up kernel: rare off-by-one tiles, see DESIGN.md section 8"))
 
 
